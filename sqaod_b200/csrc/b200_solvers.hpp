@@ -1,0 +1,113 @@
+/* b200_solvers.hpp -- concrete solver classes of the B200 back end (internal header). */
+#pragma once
+#include "device.hpp"
+#include <vector>
+
+namespace sqb {
+
+/* ---- device-side formulas (formulas.cu) ---- */
+/* h = -1/2 colsum(sW), J = -1/4 sW with zero diagonal, c = sum(J before zeroing) + sum(diag)   (s = +-1) */
+template <class real>
+void devDenseHamiltonian(const B200Device &dev, real *d_h, real *d_J, int ldJ, real *d_c, const real *d_W, int ldW, int N, real sign);
+template <class real>
+void devBipartiteHamiltonian(const B200Device &dev, real *d_h0, real *d_h1, real *d_J, int ldJ, real *d_c, const real *d_b0,
+                             const real *d_b1, const real *d_W, int ldW, int N0, int N1, real sign);
+/* E_b = alpha * ( sum_i v_bi (g_i + sum_j A_ij u_bj) + sum_j f_j u_bj ) + beta0 ; A is R x C, u is nBatch x C, v is nBatch x R
+ * (g, f may be NULL).  Dense Ising: u = v = q, g = h.  QUBO: u = v = x.  Bipartite: A = J (N1 x N0), u = q0, v = q1. */
+template <class real>
+void devBatchedEnergy(const B200Device &dev, real *d_E, const real *d_A, int ldA, int R, int C, const signed char *d_u, int ldu,
+                      const signed char *d_v, int ldv, const real *d_g, const real *d_f, int nBatch, real alpha, real beta0);
+/* E[i1][i0] = b0.x0_i0 + b1.x1_i1 + x1_i1^T W x0_i0 */
+template <class real>
+void devBipartiteEnergy2D(const B200Device &dev, real *d_E, int ldE, const real *d_b0, const real *d_b1, const real *d_W, int ldW,
+                          int N0, int N1, const signed char *d_x0, int ldx0, int n0, const signed char *d_x1, int ldx1, int n1);
+
+void launchRandomizeSpin(const B200Device &dev, signed char *q, int ldq, int N, int m, unsigned long long seed,
+                         unsigned long long count, unsigned domain);
+long long ringSpinDot(const B200Device &dev, const signed char *q, int ldq, int N, int m);
+
+/* extras of the dense brute-force searcher reachable through the C ABI (sharded search) */
+struct DenseBFExtras {
+    virtual ~DenseBFExtras() {}
+    virtual void setRange(sq::PackedBitSet xBegin, sq::PackedBitSet xEnd) = 0;
+    virtual double getEmin() const = 0;
+    virtual const sq::PackedBitSetArray &packedSolutions() const = 0;
+    virtual void setPackedSolutions(double Emin, const sq::PackedBitSet *x, int n) = 0;
+};
+
+/* ---- dense-graph annealer ---- */
+template <class real> class B200DenseGraphAnnealer : public sq::cuda::DenseGraphAnnealer<real> {
+    typedef sq::MatrixType<real> HostMatrix;
+    typedef sq::VectorType<real> HostVector;
+    typedef B200DenseGraphAnnealer<real> This;
+    typedef sq::DenseGraphAnnealer<real> Base;
+public:
+    B200DenseGraphAnnealer();
+    ~B200DenseGraphAnnealer();
+    void assignDevice(sq::cuda::Device &device);
+    sq::Algorithm selectAlgorithm(sq::Algorithm algo);
+    void seed(unsigned long long seed);
+    void setQUBO(const HostMatrix &W, sq::OptimizeMethod om = sq::optMinimize);
+    void setHamiltonian(const HostVector &h, const HostMatrix &J, real c = real(0.));
+    void getHamiltonian(HostVector *h, HostMatrix *J, real *c) const;
+    sq::Preferences getPreferences() const;
+    const HostVector &get_E() const;
+    const sq::BitSetArray &get_x() const;
+    void set_q(const sq::BitSet &q);
+    void set_qset(const sq::BitSetArray &q);
+    const sq::BitSetArray &get_q() const;
+    void randomizeSpin();
+    void prepare();
+    void calculate_E();
+    void makeSolution();
+    real getSystemE(real G, real beta) const;
+    void annealOneStep(real G, real beta);
+
+    /* extras used by the C ABI */
+    void setSpinsRaw(const signed char *q, int m);
+    void getSpinsRaw(signed char *q) const;
+    void getStats(unsigned long long *accepted, unsigned long long *waits) const;
+    int numTrotters() const { return m_; }
+    B200Device *device() const { return dev_; }
+
+private:
+    void uploadProblem(const real *h, const real *J, int strideJ);
+    void syncBits();
+
+    B200Device *dev_;
+    DevBuf<real> dJ_, dh_, dE_;
+    DevBuf<signed char> dq_;
+    DevBuf<unsigned long long> dAcceptFlags_, dSnapFlags_, dSnapBits_, dStats_;
+    int ldJ_, ldq_;
+    real c_;
+    unsigned long long seed_, step_, randomizeCount_, launchCount_;
+    int grid_, chunkElems_, chunksPerRow_, stages_, nw64_, nWindows_;
+    size_t smemBytes_;
+    HostVector E_;
+    std::vector<signed char> hq_;
+    sq::BitSetArray xlist_, qlist_;
+
+    using Base::selectDefaultAlgorithm;
+    using Base::selectDefaultSAAlgorithm;
+    using Base::N_;
+    using Base::m_;
+    using Base::om_;
+    using Base::algo_;
+    using Base::solRandSeedGiven;
+    using Base::solPrepared;
+    using Base::solProblemSet;
+    using Base::solQSet;
+    using Base::solEAvailable;
+    using Base::solSolutionAvailable;
+    using Base::setState;
+    using Base::clearState;
+    using Base::isRandSeedGiven;
+    using Base::isPrepared;
+    using Base::isEAvailable;
+    using Base::isSolutionAvailable;
+    using Base::throwErrorIfProblemNotSet;
+    using Base::throwErrorIfNotPrepared;
+    using Base::throwErrorIfQNotSet;
+};
+
+} // namespace sqb

@@ -1,0 +1,778 @@
+/* dense_annealer.cu -- dense-graph SQA / SA annealer for B200 (sm_100a).
+ *
+ * Replaces the reference's CUDADenseGraphAnnealer (sqaodc/cuda/CUDADenseGraphAnnealer.cu:128-602) together with its
+ * J.q reduction kernels (DeviceSegmentedSum.cuh, DeviceBatchedDot.cuh:211-262), flip kernels (:428-480, :543-561) and
+ * random-number pool (DeviceRandomBuffer.cu).  The Markov chain is the reference CPU solver's
+ * (sqaodc/cpu/CPUDenseGraphAnnealer.cpp:250-338): per annealOneStep N rounds; in each round every trotter y draws a
+ * spin x and a uniform u and does one Metropolis attempt with
+ *     dE = (2/m) q_yx (h_x + 2 sum_j J_xj q_yj) - q_yx (q_{y-1,x} + q_{y+1,x}) coef,   coef = ln tanh(G beta/m)/beta
+ * even trotters first, then (m odd) trotter m-1, then odd trotters.  (x, u) come from Philox keyed by
+ * (seed, step, round, y) instead of per-thread MT19937 streams, so the trajectory is a pure function of the seed and
+ * is reproduced bit for bit by the CPU oracle in "philox" mode (tests/test_dense_annealer_gpu.py).
+ *
+ * ONE persistent cooperative kernel per annealOneStep (the reference needs 2N dependent launches):
+ *   - CTA c owns T contiguous trotters (m spread over min(#SM, m) CTAs); their spins live bit-packed in shared memory.
+ *   - 8 "dot" warps stream the J rows the owned trotters will need, K=16 rounds ahead of the accept chain, through
+ *     per-warp rings of TMA bulk copies (cp.async.bulk + mbarrier), and reduce sum_j J_xj q_yj against a SNAPSHOT of
+ *     q_y with warp shuffles.  Flip positions are state-independent, so rows are known arbitrarily far ahead.
+ *   - because at most one spin per trotter changes per round, the dot product against the stale snapshot is repaired
+ *     exactly with one term per accepted flip since the snapshot: -2 q_old[x'] J[x][x'].  The J[x][x'] cross terms are
+ *     picked out of the row while it sits in shared memory (one per lane, <= 2K-1 = 31 of them).
+ *   - 1 "chain" warp (lane = trotter) replays the K rounds in the reference's order using the finished dot products,
+ *     the cross terms and the neighbours' spins.  Neighbours inside the CTA are read from shared memory; for the two
+ *     trotters owned by other CTAs the chain uses a published snapshot plus the accept bits of exactly those
+ *     neighbour attempts that hit the same spin index (probability ~K/N per attempt), so there is no per-round grid
+ *     barrier: CTAs meet only through per-window snapshots and rare per-attempt flag waits (L2, release/acquire).
+ * HBM traffic is one J row per attempt (N*sizeof(real) bytes), the figure SURVEY.md section 8(d) uses.
+ */
+#include "device.hpp"
+#include "kernels_common.cuh"
+#include "philox.cuh"
+#include "b200_solvers.hpp"
+#include <math.h>
+#include <time.h>
+#include <algorithm>
+
+namespace sqb {
+
+enum { SW_K = 16, SW_DOT_WARPS = 8, SW_THREADS = (SW_DOT_WARPS + 1) * 32, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4 };
+
+template <class real> struct SweepParams {
+    const real *J;
+    const real *h;
+    signed char *q;
+    int ldJ, ldq, N, m;
+    unsigned long long seed, step;
+    real twoDivM, coef, beta;
+    int chunkElems, chunksPerRow, stages, nw64;
+    unsigned long long *acceptFlags; /* [m][SW_FLAG_RING] */
+    unsigned long long *snapFlags;   /* [m] */
+    unsigned long long *snapBits;    /* [m][SW_SNAP_SLOTS][nw64] */
+    unsigned long long roundBase, snapBase;
+    unsigned long long *stats;       /* [0] accepted flips, [1] remote waits */
+};
+
+/* shared-memory carve-up, identical on host and device */
+template <class real> struct SweepSmem {
+    size_t ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, us, hs, xn, conf, total;
+    __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages) {
+        size_t o = 0;
+        ring = o; o += (size_t)SW_DOT_WARPS * stages * chunkElems * sizeof(real);
+        bars = o; o += (size_t)SW_DOT_WARPS * stages * 8;
+        qcur = o; o += (size_t)T * nw64 * 8;
+        qsnap = o; o += (size_t)T * nw64 * 8;
+        nbsnap = o; o += (size_t)2 * nw64 * 8;
+        dots = o; o += (size_t)2 * T * SW_K * sizeof(real);
+        o = (o + 15) & ~(size_t)15;
+        cross = o; o += (size_t)2 * T * SW_K * 32 * sizeof(real);
+        xs = o; o += (size_t)3 * T * SW_K * 4;
+        o = (o + 15) & ~(size_t)15;
+        us = o; o += (size_t)3 * T * SW_K * sizeof(real);
+        hs = o; o += (size_t)3 * T * SW_K * sizeof(real);
+        xn = o; o += (size_t)2 * 3 * SW_K * 4;
+        conf = o; o += (size_t)2 * SW_K * 4;
+        total = (o + 127) & ~(size_t)127;
+    }
+};
+
+template <class real> __device__ __forceinline__ real expReal(real v);
+template <> __device__ __forceinline__ float expReal<float>(float v) { return expf(v); }
+template <> __device__ __forceinline__ double expReal<double>(double v) { return exp(v); }
+
+/* accumulate the signed sum of one 128-spin group: lane owns 4 consecutive elements */
+__device__ __forceinline__ void accumGroup(const float *buf, uint32_t nib, float &a0, float &a1, float &a2, float &a3) {
+    float4 v = *reinterpret_cast<const float4 *>(buf);
+    uint32_t neg = ~nib; /* bit set -> spin +1 -> keep sign */
+    a0 += signFlip(v.x, neg << 31);
+    a1 += signFlip(v.y, neg << 30);
+    a2 += signFlip(v.z, neg << 29);
+    a3 += signFlip(v.w, neg << 28);
+}
+__device__ __forceinline__ void accumGroup(const double *buf, uint32_t nib, double &a0, double &a1, double &a2, double &a3) {
+    double2 v0 = *reinterpret_cast<const double2 *>(buf);
+    double2 v1 = *reinterpret_cast<const double2 *>(buf + 2);
+    uint32_t neg = ~nib;
+    a0 += signFlip(v0.x, neg << 31);
+    a1 += signFlip(v0.y, neg << 30);
+    a2 += signFlip(v1.x, neg << 29);
+    a3 += signFlip(v1.y, neg << 28);
+}
+
+__device__ __forceinline__ int sweepPhase(int y, int m) { /* 0: even, 1: trotter m-1 of an odd ring, 2: odd */
+    if (y & 1) return 2;
+    return ((m & 1) && y == m - 1) ? 1 : 0;
+}
+
+template <class real, bool SQA>
+__global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<real> P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = P.N, m = P.m, K = SW_K;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int baseT = m / G, remT = m % G;
+    const int T = baseT + (cta < remT ? 1 : 0);
+    const int y0 = cta * baseT + min(cta, remT);
+    const int maxT = baseT + (remT ? 1 : 0);
+    const int nW = (N + K - 1) / K;
+    const int CH = P.chunkElems, CPR = P.chunksPerRow, S = P.stages, NW = P.nw64;
+    const int GPC = CH >> 7;
+
+    const SweepSmem<real> L(maxT, NW, CH, S);
+    real *ring = reinterpret_cast<real *>(smem + L.ring);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+    unsigned long long *qcur = reinterpret_cast<unsigned long long *>(smem + L.qcur);
+    unsigned long long *qsnap = reinterpret_cast<unsigned long long *>(smem + L.qsnap);
+    unsigned long long *nbsnap = reinterpret_cast<unsigned long long *>(smem + L.nbsnap);
+    real *dots = reinterpret_cast<real *>(smem + L.dots);    /* [2][maxT][K] */
+    real *cross = reinterpret_cast<real *>(smem + L.cross);  /* [2][maxT][K][32] */
+    int *xs = reinterpret_cast<int *>(smem + L.xs);          /* [3][maxT][K] */
+    real *us = reinterpret_cast<real *>(smem + L.us);
+    real *hs = reinterpret_cast<real *>(smem + L.hs);
+    int *xn = reinterpret_cast<int *>(smem + L.xn);          /* [2 sides][3][K] */
+    uint32_t *conf = reinterpret_cast<uint32_t *>(smem + L.conf); /* [2][K] */
+
+    /* trotters of other CTAs adjacent to this CTA's range (SQA only) */
+    const int yLeft = (y0 == 0) ? m - 1 : y0 - 1;
+    const int yRight = (y0 + T >= m) ? 0 : y0 + T;
+    const bool remote = SQA && (G > 1);
+
+    auto roundsIn = [&](int w) { return min(K, N - w * K); };
+
+    /* (x, u, h[x]) of every attempt of window w for the owned trotters, plus the remote neighbours' x */
+    auto prepWindow = [&](int w, int t0, int nthr) {
+        if (w >= nW) return;
+        const int Kw = roundsIn(w), slot = w % 3;
+        for (int idx = t0; idx < Kw * T; idx += nthr) {
+            int t = idx % T, rl = idx / T;
+            Philox4 p = sqbPhilox(P.seed, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)(y0 + t));
+            int x = (int)(p.w[0] % (uint32_t)N);
+            int o = (slot * maxT + t) * K + rl;
+            xs[o] = x;
+            us[o] = philoxUniform<real>(p);
+            hs[o] = P.h[x];
+        }
+        if (remote) {
+            for (int idx = t0; idx < 2 * Kw; idx += nthr) {
+                int side = idx / Kw, rl = idx % Kw;
+                Philox4 p = sqbPhilox(P.seed, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)(side ? yRight : yLeft));
+                xn[(side * 3 + slot) * K + rl] = (int)(p.w[0] % (uint32_t)N);
+            }
+        }
+    };
+
+    /* ---------------- setup ---------------- */
+    for (int i = tid; i < maxT * NW; i += SW_THREADS) qcur[i] = 0ull;
+    for (int i = tid; i < 2 * NW; i += SW_THREADS) nbsnap[i] = 0ull;
+    if (tid == 0) {
+        for (int i = 0; i < SW_DOT_WARPS * S; ++i) mbarInit(&bars[i], 1);
+        mbarInitFence();
+    }
+    __syncthreads();
+    {   /* pack int8 spins -> bits; 4 spins (one nibble) per thread step */
+        const int n4 = (N + 3) >> 2;
+        const int rows = T + (remote ? 2 : 0);
+        for (int idx = tid; idx < rows * n4; idx += SW_THREADS) {
+            int r = idx / n4, j = (idx % n4) << 2;
+            int y = (r < T) ? (y0 + r) : (r == T ? yLeft : yRight);
+            const signed char *src = P.q + (size_t)y * P.ldq + j;
+            unsigned nib = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j + e < N && src[e] > 0) nib |= 1u << e;
+            int w64, bit;
+            spinBitPos(j, w64, bit);
+            unsigned long long *dst = (r < T) ? (qcur + (size_t)r * NW) : (nbsnap + (size_t)(r - T) * NW);
+            atomicOr(&dst[w64], (unsigned long long)nib << bit);
+        }
+    }
+    prepWindow(0, tid, SW_THREADS);
+    prepWindow(1, tid, SW_THREADS);
+    __syncthreads();
+    for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
+    __syncthreads();
+
+    /* ---------------- dot warps: per-warp TMA ring state ---------------- */
+    /* task = (window w, id = rl * T + t); warp d owns ids d, d + 8, ... of every window */
+    int iw = 0, iid = warp, ic = 0, ix = 0; /* issue cursor (lane 0) */
+    unsigned issued = 0, consumed = 0;
+    bool issueDone = false;
+    uint64_t *myBars = bars + warp * S;
+    real *myRing = ring + (size_t)warp * S * CH;
+
+    auto skipEmptyWindows = [&](int &w, int &id) {
+        while (w < nW && id >= roundsIn(w) * T) { ++w; id = warp; }
+    };
+    auto issueNext = [&]() { /* lane 0 of a dot warp */
+        if (issueDone) return;
+        if (ic == 0) {
+            skipEmptyWindows(iw, iid);
+            if (iw >= nW) { issueDone = true; return; }
+            int t = iid % T, rl = iid / T;
+            Philox4 p = sqbPhilox(P.seed, P.step, DOM_DENSE_SWEEP, (uint32_t)(iw * K + rl), (uint32_t)(y0 + t));
+            ix = (int)(p.w[0] % (uint32_t)N);
+        }
+        int stage = issued % S;
+        int elems = min(CH, P.ldJ - ic * CH);
+        uint32_t bytes = (uint32_t)(elems * sizeof(real));
+        mbarArriveExpectTx(&myBars[stage], bytes);
+        tmaLoad1D(myRing + (size_t)stage * CH, P.J + (size_t)ix * P.ldJ + (size_t)ic * CH, bytes, &myBars[stage]);
+        ++issued;
+        if (++ic == CPR) { ic = 0; iid += SW_DOT_WARPS; }
+    };
+    if (warp < SW_DOT_WARPS && lane == 0)
+        for (int s = 0; s < S; ++s) issueNext();
+
+    /* consume every task this warp owns in window w; results go to buffer w & 1 */
+    auto dotWindow = [&](int w) {
+        const int Kw = roundsIn(w), buf = w & 1;
+        for (int id = warp; id < Kw * T; id += SW_DOT_WARPS) {
+            const int t = id % T, rl = id / T;
+            /* column whose J[x][col] this lane must pick up: lane j < K -> round j of window w-1, else round j-K of w */
+            int px = -1;
+            if (lane < K) { if (w > 0) px = xs[(((w - 1) % 3) * maxT + t) * K + lane]; }
+            else if (lane - K < rl) px = xs[((w % 3) * maxT + t) * K + (lane - K)];
+            real crossv = real(0);
+            real a0 = real(0), a1 = real(0), a2 = real(0), a3 = real(0);
+            const unsigned long long *qrow = qsnap + (size_t)t * NW;
+            for (int c = 0; c < CPR; ++c) {
+                const int stage = consumed % S;
+                mbarWait(&myBars[stage], (consumed / S) & 1);
+                const real *buf_ = myRing + (size_t)stage * CH;
+                const int c0 = c * CH;
+                const int groups = min(GPC, (P.ldJ - c0) >> 7);
+                const int g0 = c * GPC;
+                unsigned long long bits = qrow[((g0 >> 4) << 5) + lane] >> ((g0 & 15) << 2);
+                const real *src = buf_ + lane * 4;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (i < groups) accumGroup(src + i * 128, (uint32_t)(bits >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+                }
+                if (px >= c0 && px < c0 + (groups << 7)) crossv = buf_[px - c0];
+                __syncwarp();
+                if (lane == 0) issueNext();
+                ++consumed;
+            }
+            real s = warpSum((a0 + a1) + (a2 + a3));
+            if (lane == 0) dots[(buf * maxT + t) * K + rl] = s;
+            cross[((buf * maxT + t) * K + rl) * 32 + lane] = crossv;
+        }
+    };
+
+    /* prologue: dot products of window 0 (against the launch state) */
+    if (warp < SW_DOT_WARPS) dotWindow(0);
+    __syncthreads();
+
+    /* ---------------- chain warp state ---------------- */
+    const bool chainWarp = (warp == SW_DOT_WARPS);
+    const bool active = chainWarp && (lane < T);
+    const int y = y0 + lane;
+    const int myPhase = sweepPhase(y, m);
+    const int yl = (y == 0) ? m - 1 : y - 1, yr = (y == m - 1) ? 0 : y + 1;
+    const bool lLocal = (yl >= y0 && yl < y0 + T), rLocal = (yr >= y0 && yr < y0 + T);
+    uint32_t accP = 0, sgnP = 0, accC = 0, sgnC = 0;
+    unsigned long long nAccepted = 0, nWaits = 0;
+
+    /* spin of a trotter owned by another CTA: published snapshot, corrected by the accept bits of the neighbour's
+     * attempts that hit the same spin index since the snapshot */
+    auto remoteSpin = [&](int side, int x, int w, int rl) -> int {
+        int v = spinAt(nbsnap + (size_t)side * NW, x);
+        uint32_t mask = conf[side * K + rl];
+        if (mask) {
+            const int yn = side ? yRight : yLeft;
+            const int nbPhase = sweepPhase(yn, m);
+            uint32_t vis = (w > 0 ? 0xffffu : 0u) | (((1u << rl) - 1u) << K) | ((nbPhase < myPhase) ? (1u << (K + rl)) : 0u);
+            mask &= vis;
+            while (mask) {
+                int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                long long rr = (long long)w * K + (j - K); /* j < K: previous window */
+                const unsigned long long want = P.roundBase + (unsigned long long)rr + 1ull;
+                const unsigned long long *f = P.acceptFlags + (size_t)yn * SW_FLAG_RING + (rr % SW_FLAG_RING);
+                unsigned long long got = ldAcquire(f);
+                while ((got >> 1) != want) { ++nWaits; __nanosleep(20); got = ldAcquire(f); }
+                if (got & 1ull) v = -v;
+            }
+        }
+        return v;
+    };
+
+    for (int w = 0; w < nW; ++w) {
+        if (warp < SW_DOT_WARPS) {
+            if (w + 1 < nW) dotWindow(w + 1);
+        } else {
+            /* ---- chain warp ---- */
+            const int Kw = roundsIn(w), buf = w & 1, slot = w % 3;
+            if (remote) {
+                if (w >= 2) { /* neighbours' snapshot S_{w-1} (state before window w-1) */
+                    for (int side = 0; side < 2; ++side) {
+                        const int yn = side ? yRight : yLeft;
+                        if (lane == 0) {
+                            const unsigned long long want = P.snapBase + (unsigned long long)(w - 1);
+                            while (ldAcquire(P.snapFlags + yn) < want) { ++nWaits; __nanosleep(50); }
+                        }
+                        __syncwarp();
+                        const unsigned long long *src = P.snapBits + ((size_t)yn * SW_SNAP_SLOTS + ((w - 1) % SW_SNAP_SLOTS)) * NW;
+                        for (int i = lane; i < NW; i += 32) nbsnap[(size_t)side * NW + i] = __ldcg(src + i);
+                    }
+                }
+                /* which neighbour attempts (previous + current window) hit the spin index of my attempt rl */
+                for (int side = 0; side < 2; ++side) {
+                    int nbx = -1;
+                    if (lane < K) { if (w > 0) nbx = xn[(side * 3 + (w - 1) % 3) * K + lane]; }
+                    else if (lane - K < Kw) nbx = xn[(side * 3 + slot) * K + (lane - K)];
+                    const int tEdge = side ? T - 1 : 0;
+                    for (int rl = 0; rl < Kw; ++rl) {
+                        int xe = xs[(slot * maxT + tEdge) * K + rl];
+                        uint32_t hit = __ballot_sync(0xffffffffu, nbx == xe);
+                        if (lane == 0) conf[side * K + rl] = hit;
+                    }
+                }
+            }
+            __syncwarp();
+            /* (x, u, h) two windows ahead; reuses the ring slot of window w-1, so only after the masks above */
+            prepWindow(w + 2, lane, 32);
+            __syncwarp();
+            for (int rl = 0; rl < Kw; ++rl) {
+#pragma unroll 1
+                for (int ph = 0; ph < 3; ++ph) {
+                    if (ph == 1 && !(m & 1)) continue;
+                    if (active && myPhase == ph) {
+                        const int o = (slot * maxT + lane) * K + rl;
+                        const int x = xs[o];
+                        int w64, bit;
+                        spinBitPos(x, w64, bit);
+                        unsigned long long *word = qcur + (size_t)lane * NW + w64;
+                        const bool up = ((*word >> bit) & 1ull) != 0;
+                        const real qyx = up ? real(1) : real(-1);
+                        /* repair the snapshot dot product with every flip accepted since the snapshot */
+                        real sum = dots[(buf * maxT + lane) * K + rl];
+                        const real *cr = cross + ((buf * maxT + lane) * K + rl) * 32;
+                        uint32_t ev = accP | ((accC & ((1u << rl) - 1u)) << K);
+                        const uint32_t sg = sgnP | (sgnC << K);
+                        while (ev) {
+                            int j = __ffs(ev) - 1;
+                            ev &= ev - 1;
+                            real qold = ((sg >> j) & 1u) ? real(1) : real(-1);
+                            sum += real(-2) * qold * cr[j];
+                        }
+                        real dE;
+                        if (SQA) {
+                            int ql = lLocal ? spinAt(qcur + (size_t)(yl - y0) * NW, x) : remoteSpin(0, x, w, rl);
+                            int qr = rLocal ? spinAt(qcur + (size_t)(yr - y0) * NW, x) : remoteSpin(1, x, w, rl);
+                            dE = P.twoDivM * qyx * (hs[o] + real(2) * sum);
+                            dE -= qyx * real(ql + qr) * P.coef;
+                        } else {
+                            dE = real(2) * qyx * (hs[o] + real(2) * sum);
+                        }
+                        const real thr = (dE < real(0)) ? real(1) : expReal<real>(-dE * P.beta);
+                        const bool acc = thr > us[o];
+                        if (acc) {
+                            *word ^= (1ull << bit);
+                            accC |= 1u << rl;
+                            if (up) sgnC |= 1u << rl;
+                            ++nAccepted;
+                        }
+                        if (remote && (lane == 0 || lane == T - 1)) {
+                            const unsigned long long rr = (unsigned long long)w * K + rl;
+                            stRelease(P.acceptFlags + (size_t)y * SW_FLAG_RING + (rr % SW_FLAG_RING),
+                                      ((P.roundBase + rr + 1ull) << 1) | (acc ? 1ull : 0ull));
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            accP = accC; sgnP = sgnC; accC = 0; sgnC = 0;
+        }
+        __syncthreads();
+        /* new snapshot S_{w+1}; publish the edge trotters for the neighbouring CTAs */
+        for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
+        if (remote && w + 1 < nW) {
+            const int nEdge = (T > 1) ? 2 : 1;
+            for (int i = tid; i < nEdge * NW; i += SW_THREADS) {
+                int e = i / NW, k = i % NW;
+                int t = e ? T - 1 : 0;
+                P.snapBits[((size_t)(y0 + t) * SW_SNAP_SLOTS + ((w + 1) % SW_SNAP_SLOTS)) * NW + k] = qcur[(size_t)t * NW + k];
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (remote && w + 1 < nW && tid == 0) {
+            stRelease(P.snapFlags + y0, P.snapBase + (unsigned long long)(w + 1));
+            if (T > 1) stRelease(P.snapFlags + y0 + T - 1, P.snapBase + (unsigned long long)(w + 1));
+        }
+    }
+
+    /* ---------------- write the spins back ---------------- */
+    {
+        const int n4 = (N + 3) >> 2;
+        for (int idx = tid; idx < T * n4; idx += SW_THREADS) {
+            int r = idx / n4, j = (idx % n4) << 2;
+            int w64, bit;
+            spinBitPos(j, w64, bit);
+            unsigned nib = (unsigned)(qcur[(size_t)r * NW + w64] >> bit) & 0xfu;
+            signed char *dst = P.q + (size_t)(y0 + r) * P.ldq + j;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j + e < N) dst[e] = ((nib >> e) & 1u) ? 1 : -1;
+        }
+    }
+    if (chainWarp && P.stats) {
+        nAccepted = warpSum(nAccepted);
+        nWaits = warpSum(nWaits);
+        if (lane == 0) {
+            atomicAdd(P.stats, nAccepted);
+            atomicAdd(P.stats + 1, nWaits);
+        }
+    }
+}
+
+/* ---------------- small element-wise kernels ---------------- */
+__global__ void randomizeSpinKernel(signed char *q, int ldq, int N, int m, unsigned long long seed,
+                                    unsigned long long count, unsigned domain) {
+    /* one Philox call per 128 spins (reference: DeviceKernels.cu:549-572 takes the LSB of a pool word per spin) */
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int groups = (N + 127) >> 7;
+    if (g >= groups * m) return;
+    int y = g / groups, grp = g % groups;
+    Philox4 p = sqbPhilox(seed, count, domain, (uint32_t)grp, (uint32_t)y);
+    signed char *row = q + (size_t)y * ldq;
+    int x0 = grp << 7;
+    for (int k = 0; k < 128 && x0 + k < N; ++k) row[x0 + k] = ((p.w[(k >> 5) & 3] >> (k & 31)) & 1u) ? 1 : -1;
+}
+
+__global__ void broadcastSpinRowKernel(signed char *q, int ldq, int N, int m, const signed char *src) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < N && y < m) q[(size_t)y * ldq + x] = src[x];
+}
+
+/* sum_y q_y . q_{(y+1) mod m}  (reference: DeviceBatchedDot.cuh:62-74, 144-160) */
+__global__ void ringSpinDotKernel(const signed char *q, int ldq, int N, int m, long long *out) {
+    int y = blockIdx.x;
+    const signed char *a = q + (size_t)y * ldq, *b = q + (size_t)((y + 1) % m) * ldq;
+    int s = 0;
+    for (int x = threadIdx.x; x < N; x += blockDim.x) s += (int)a[x] * (int)b[x];
+    s = warpSum(s);
+    if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)out, (unsigned long long)(long long)s);
+}
+
+void launchRandomizeSpin(const B200Device &dev, signed char *q, int ldq, int N, int m, unsigned long long seed,
+                         unsigned long long count, unsigned domain) {
+    int groups = ((N + 127) >> 7) * m;
+    randomizeSpinKernel<<<(groups + 127) / 128, 128, 0, dev.stream()>>>(q, ldq, N, m, seed, count, domain);
+    CUDA_CHECK(cudaGetLastError());
+    ++dev.launchCount;
+}
+
+long long ringSpinDot(const B200Device &dev, const signed char *q, int ldq, int N, int m) {
+    DevBuf<long long> d;
+    d.alloc(&dev, 1);
+    ringSpinDotKernel<<<m, 128, 0, dev.stream()>>>(q, ldq, N, m, d.p);
+    CUDA_CHECK(cudaGetLastError());
+    ++dev.launchCount;
+    long long h = 0;
+    dev.d2h(&h, d.p, sizeof(h));
+    dev.synchronize();
+    return h;
+}
+
+/* =====================================================================================
+ * host class
+ * ===================================================================================== */
+template <class real> B200DenseGraphAnnealer<real>::B200DenseGraphAnnealer()
+    : dev_(NULL), ldJ_(0), ldq_(0), c_(0), seed_(0), step_(0), randomizeCount_(0), launchCount_(0), nWindows_(0) {
+    m_ = -1;
+    selectAlgorithm(sq::algoDefault);
+}
+template <class real> B200DenseGraphAnnealer<real>::~B200DenseGraphAnnealer() {}
+
+template <class real> void B200DenseGraphAnnealer<real>::assignDevice(sq::cuda::Device &device) {
+    sqb_throwErrorIf(dev_ != NULL, "Device assigned more than once.");
+    dev_ = &asB200(device);
+}
+
+template <class real> sq::Algorithm B200DenseGraphAnnealer<real>::selectAlgorithm(sq::Algorithm algo) {
+    /* same table as CUDADenseGraphAnnealer.cu:114-126: coloring and sa_naive are native, the rest fall back */
+    switch (algo) {
+    case sq::algoColoring:
+    case sq::algoSANaive:
+        algo_ = algo;
+        break;
+    default:
+        selectDefaultAlgorithm(algo, sq::algoColoring, sq::algoSANaive);
+        break;
+    }
+    return algo_;
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::seed(unsigned long long seed) {
+    sqb_throwErrorIf(dev_ == NULL, "Device not set.");
+    seed_ = seed;
+    step_ = 0;
+    randomizeCount_ = 0;
+    setState(solRandSeedGiven);
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::uploadProblem(const real *h, const real *J, int strideJ) {
+    ldJ_ = sq::roundUp(N_, 128);
+    dJ_.alloc(dev_, (size_t)N_ * ldJ_);
+    dh_.alloc(dev_, N_);
+    dev_->h2d2D(dJ_.p, sizeof(real) * ldJ_, J, sizeof(real) * strideJ, sizeof(real) * N_, N_);
+    dev_->h2d(dh_.p, h, sizeof(real) * N_);
+    dev_->synchronize();
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::setQUBO(const HostMatrix &W, sq::OptimizeMethod om) {
+    sqb_throwErrorIf(W.rows != W.cols, "%s, W is not a sqare matrix.", __func__);
+    sqb_throwErrorIf(!sq::isSymmetric(W), "%s, Matrix is not symmetric.", __func__);
+    sqb_throwErrorIf(dev_ == NULL, "Device not set.");
+    clearState(solProblemSet);
+    N_ = W.rows;
+    m_ = N_ / 4;
+    om_ = om;
+    /* QUBO -> Ising on the device (formulas.cu); maximize negates W first (CUDADenseGraphAnnealer.cu:148-149) */
+    ldJ_ = sq::roundUp(N_, 128);
+    dJ_.alloc(dev_, (size_t)N_ * ldJ_);
+    dh_.alloc(dev_, N_);
+    DevBuf<real> dW, dc;
+    dW.alloc(dev_, (size_t)N_ * ldJ_);
+    dc.alloc(dev_, 1);
+    dev_->h2d2D(dW.p, sizeof(real) * ldJ_, W.data, sizeof(real) * W.stride, sizeof(real) * N_, N_);
+    devDenseHamiltonian<real>(*dev_, dh_.p, dJ_.p, ldJ_, dc.p, dW.p, ldJ_, N_, om == sq::optMaximize ? real(-1) : real(1));
+    dev_->d2h(&c_, dc.p, sizeof(real));
+    dev_->synchronize();
+    setState(solProblemSet);
+}
+
+template <class real>
+void B200DenseGraphAnnealer<real>::setHamiltonian(const HostVector &h, const HostMatrix &J, real c) {
+    sqb_throwErrorIf(J.rows != J.cols || h.size != J.rows, "%s, shape mismatch between h and J.", __func__);
+    sqb_throwErrorIf(!sq::isSymmetric(J), "%s, Matrix is not symmetric.", __func__);
+    sqb_throwErrorIf(dev_ == NULL, "Device not set.");
+    clearState(solProblemSet);
+    N_ = J.rows;
+    m_ = N_ / 4;
+    om_ = sq::optMinimize;
+    c_ = c;
+    uploadProblem(h.data, J.data, J.stride);
+    setState(solProblemSet);
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::getHamiltonian(HostVector *h, HostMatrix *J, real *c) const {
+    throwErrorIfProblemNotSet();
+    h->resize(N_);
+    J->resize(N_, N_);
+    dev_->d2h(h->data, dh_.p, sizeof(real) * N_);
+    dev_->d2h2D(J->data, sizeof(real) * J->stride, dJ_.p, sizeof(real) * ldJ_, sizeof(real) * N_, N_);
+    dev_->synchronize();
+    *c = c_;
+}
+
+template <class real> sq::Preferences B200DenseGraphAnnealer<real>::getPreferences() const {
+    sq::Preferences prefs = Base::getPreferences();
+    prefs.pushBack(sq::Preference(sq::pnDevice, "cuda"));
+    return prefs;
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::prepare() {
+    throwErrorIfProblemNotSet();
+    sqb_throwErrorIf(m_ <= 0, "# trotters must be a positive integer.");
+    sqb_throwErrorIf(m_ > 32 * dev_->numSMs(), "nTrotters too large for this device.");
+    if (!isRandSeedGiven()) seed((unsigned long long)time(NULL));
+    setState(solRandSeedGiven);
+    if (m_ == 1) selectDefaultSAAlgorithm(algo_, sq::algoSANaive);
+
+    ldq_ = sq::roundUp(N_, 16);
+    dq_.alloc(dev_, (size_t)m_ * ldq_);
+    dE_.alloc(dev_, m_);
+    E_.resize(m_);
+    hq_.assign((size_t)m_ * ldq_, 0);
+
+    /* launch geometry of the sweep */
+    const int G = std::min(dev_->numSMs(), (int)m_);
+    const int maxT = (m_ + G - 1) / G;
+    const int nw64 = packedWords64(N_);
+    int chunkElems = std::min((int)ldJ_, (int)(8192 / sizeof(real)));
+    int stages = 3;
+    for (;;) {
+        SweepSmem<real> L(maxT, nw64, chunkElems, stages);
+        if (L.total <= dev_->smemPerBlockOptin()) break;
+        if (stages > 2) --stages;
+        else if (chunkElems > 128) chunkElems >>= 1;
+        else sqb_throwError("problem too large for the sweep kernel's shared memory (N=%d, m=%d).", N_, m_);
+    }
+    grid_ = G;
+    chunkElems_ = chunkElems;
+    chunksPerRow_ = (ldJ_ + chunkElems - 1) / chunkElems;
+    stages_ = stages;
+    nw64_ = nw64;
+    smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages).total;
+    nWindows_ = (N_ + SW_K - 1) / SW_K;
+    dAcceptFlags_.alloc(dev_, (size_t)m_ * SW_FLAG_RING);
+    dSnapFlags_.alloc(dev_, m_);
+    dSnapBits_.alloc(dev_, (size_t)m_ * SW_SNAP_SLOTS * nw64);
+    dStats_.alloc(dev_, 2);
+    launchCount_ = 0;
+    CUDA_CHECK(cudaFuncSetAttribute(denseSweepKernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
+    CUDA_CHECK(cudaFuncSetAttribute(denseSweepKernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
+    xlist_.clear();
+    qlist_.clear();
+    setState(solPrepared);
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::randomizeSpin() {
+    throwErrorIfNotPrepared();
+    launchRandomizeSpin(*dev_, dq_.p, ldq_, N_, m_, seed_, randomizeCount_++, DOM_RANDOMIZE);
+    setState(solQSet);
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::set_q(const sq::BitSet &q) {
+    sqb_throwErrorIf(q.size != N_, "Dimension of q, %d, should be equal to N, %d.", q.size, N_);
+    throwErrorIfNotPrepared();
+    DevBuf<signed char> tmp;
+    tmp.alloc(dev_, N_);
+    dev_->h2d(tmp.p, q.data, N_);
+    dim3 grid((N_ + 127) / 128, m_);
+    broadcastSpinRowKernel<<<grid, 128, 0, dev_->stream()>>>(dq_.p, ldq_, N_, m_, tmp.p);
+    CUDA_CHECK(cudaGetLastError());
+    ++dev_->launchCount;
+    dev_->synchronize();
+    setState(solQSet);
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::set_qset(const sq::BitSetArray &q) {
+    sqb_throwErrorIf(q.size() == 0, "empty q set.");
+    for (int i = 0; i < q.size(); ++i)
+        sqb_throwErrorIf(q[i].size != N_, "Dimension of q, %d, should be equal to N, %d.", q[i].size, N_);
+    m_ = q.size();
+    prepare(); /* CUDADenseGraphAnnealer.cu:216-218: the number of trotters follows the set */
+    for (int y = 0; y < m_; ++y) memcpy(&hq_[(size_t)y * ldq_], q[y].data, N_);
+    dev_->h2d(dq_.p, hq_.data(), hq_.size());
+    dev_->synchronize();
+    setState(solQSet);
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::setSpinsRaw(const signed char *q, int m) {
+    /* C-ABI fast path of set_qset: q is m x N, contiguous */
+    throwErrorIfProblemNotSet();
+    if (m != m_ || !isPrepared()) { m_ = m; prepare(); }
+    dev_->h2d2D(dq_.p, ldq_, q, N_, N_, m_);
+    dev_->synchronize();
+    setState(solQSet);
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::getSpinsRaw(signed char *q) const {
+    throwErrorIfQNotSet();
+    dev_->d2h2D(q, N_, dq_.p, ldq_, N_, m_);
+    dev_->synchronize();
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::syncBits() {
+    xlist_.clear();
+    qlist_.clear();
+    dev_->d2h(hq_.data(), dq_.p, hq_.size());
+    dev_->synchronize();
+    for (int y = 0; y < m_; ++y) {
+        sq::BitSet q(N_), x(N_);
+        for (int i = 0; i < N_; ++i) {
+            char v = hq_[(size_t)y * ldq_ + i];
+            q(i) = v;
+            x(i) = (char)((v + 1) / 2);
+        }
+        qlist_.pushBack(q);
+        xlist_.pushBack(x);
+    }
+}
+
+template <class real> const sq::BitSetArray &B200DenseGraphAnnealer<real>::get_x() const {
+    if (!isSolutionAvailable()) const_cast<This *>(this)->makeSolution();
+    return xlist_;
+}
+template <class real> const sq::BitSetArray &B200DenseGraphAnnealer<real>::get_q() const {
+    if (!isSolutionAvailable()) const_cast<This *>(this)->makeSolution();
+    return qlist_;
+}
+template <class real> const sq::VectorType<real> &B200DenseGraphAnnealer<real>::get_E() const {
+    if (!isEAvailable()) const_cast<This *>(this)->calculate_E();
+    return E_;
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::calculate_E() {
+    throwErrorIfQNotSet();
+    /* E_y = -c - h.q_y - q_y^T J q_y, sign-flipped for maximize (CUDADenseGraphAnnealer.cu:260-272) */
+    const real sign = (om_ == sq::optMaximize) ? real(-1) : real(1);
+    devBatchedEnergy<real>(*dev_, dE_.p, dJ_.p, ldJ_, N_, N_, dq_.p, ldq_, dq_.p, ldq_, dh_.p, NULL, m_, -sign, -sign * c_);
+    dev_->d2h(E_.data, dE_.p, sizeof(real) * m_);
+    dev_->synchronize();
+    setState(solEAvailable);
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::makeSolution() {
+    throwErrorIfQNotSet();
+    syncBits();
+    setState(solSolutionAvailable);
+    calculate_E();
+}
+
+template <class real> real B200DenseGraphAnnealer<real>::getSystemE(real G, real beta) const {
+    This *self = const_cast<This *>(this);
+    self->calculate_E();
+    real E = E_.sum() / m_;
+    if (sq::isSQAAlgorithm(algo_)) {
+        real spinDotSum = (real)ringSpinDot(*dev_, dq_.p, ldq_, N_, m_);
+        real coef = real(0.5) / beta * std::log(std::tanh(G * beta / m_));
+        E -= spinDotSum * coef;
+    }
+    if (om_ == sq::optMaximize) E *= real(-1.); /* as the reference, CUDADenseGraphAnnealer.cu:372-373 */
+    return E;
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, real beta) {
+    throwErrorIfQNotSet();
+    clearState(solSolutionAvailable);
+    SweepParams<real> P;
+    P.J = dJ_.p; P.h = dh_.p; P.q = dq_.p;
+    P.ldJ = ldJ_; P.ldq = ldq_; P.N = N_; P.m = m_;
+    P.seed = seed_; P.step = step_;
+    const bool sqa = (algo_ == sq::algoColoring);
+    if (sqa) {
+        P.twoDivM = real(2.) / real(m_);
+        P.coef = std::log(std::tanh(G * beta / m_)) / beta;
+        P.beta = beta;
+    } else { /* annealOneStep(kT, _) for SA: CUDADenseGraphAnnealer.cu:585-602 */
+        P.twoDivM = real(2.);
+        P.coef = real(0.);
+        P.beta = real(1.) / G;
+    }
+    P.chunkElems = chunkElems_; P.chunksPerRow = chunksPerRow_; P.stages = stages_; P.nw64 = nw64_;
+    P.acceptFlags = dAcceptFlags_.p; P.snapFlags = dSnapFlags_.p; P.snapBits = dSnapBits_.p;
+    P.roundBase = (launchCount_ + 1ull) * (unsigned long long)(N_ + SW_FLAG_RING);
+    P.snapBase = (launchCount_ + 1ull) * (unsigned long long)(nWindows_ + 2);
+    P.stats = dStats_.p;
+    void *args[] = {&P};
+    const void *fn = sqa ? (const void *)denseSweepKernel<real, true> : (const void *)denseSweepKernel<real, false>;
+    dev_->makeCurrent();
+    CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid_), dim3(SW_THREADS), args, smemBytes_, dev_->stream()));
+    ++dev_->launchCount;
+    ++launchCount_;
+    ++step_;
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::getStats(unsigned long long *accepted, unsigned long long *waits) const {
+    unsigned long long h[2] = {0, 0};
+    if (dStats_.p) {
+        dev_->d2h(h, dStats_.p, sizeof(h));
+        dev_->synchronize();
+    }
+    *accepted = h[0];
+    *waits = h[1];
+}
+
+template class B200DenseGraphAnnealer<float>;
+template class B200DenseGraphAnnealer<double>;
+
+} // namespace sqb
+
+namespace sqaod { namespace cuda {
+template <> DenseGraphAnnealer<float> *newDenseGraphAnnealer<float>() { return new sqb::B200DenseGraphAnnealer<float>(); }
+template <> DenseGraphAnnealer<double> *newDenseGraphAnnealer<double>() { return new sqb::B200DenseGraphAnnealer<double>(); }
+}} // namespace sqaod::cuda

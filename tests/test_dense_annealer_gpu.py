@@ -1,0 +1,163 @@
+"""GPU parity tests of the dense-graph annealer, through the C ABI (sqaod_b200 -> libsqaod_b200.so).
+
+Bar (BASELINE.json north_star): energies of identical spin configurations within 1e-5 relative (fp32) / 1e-12 (fp64);
+the sweep itself is checked two ways: (1) exact-chain -- the kernel's trajectory equals the CPU oracle's when the oracle
+draws from the same Philox stream (bit-exact spins); (2) statistically against the reference's own MT19937 chain
+(tests/test_annealer_statistics_gpu.py)."""
+import numpy as np
+import pytest
+from conftest import quantized_symmetric_W
+
+pytestmark = pytest.mark.gpu
+DT = [np.float32, np.float64]
+
+
+def tol(dtype):
+    return 1e-5 if dtype == np.float32 else 1e-12
+
+
+@pytest.fixture(scope='module')
+def sq():
+    import sqaod_b200
+    return sqaod_b200
+
+
+@pytest.mark.parametrize('dtype', DT)
+def test_hamiltonian_and_energy_vs_golden(sq, oracle, golden_dense, dtype):
+    g = golden_dense
+    for name in ('W8', 'Wr16', 'Wr12'):
+        W = g[name]
+        ann = sq.dense_graph_annealer(W, sq.minimize, dtype, n_trotters=4)
+        h, J, c = ann.get_hamiltonian()
+        assert np.allclose(h, g[name + '_h'], atol=tol(dtype) * 10)
+        assert np.allclose(J, g[name + '_J'], atol=tol(dtype))
+        assert abs(c - g[name + '_c']) <= tol(dtype) * 100
+        x = g[name + '_x']
+        q = (2 * x - 1).astype(np.int8)
+        ann.set_qset(q)                      # all 2^N configurations at once (test_dense_graph_annealer.py:98-120)
+        E = ann.get_E()
+        want = g[name + '_E_q']
+        assert np.allclose(E, want, rtol=tol(dtype), atol=tol(dtype) * 10)
+        # formulas object
+        Ex = sq.formulas.dense_graph_batch_calculate_E(W, x, dtype)
+        assert np.array_equal(Ex.astype(np.float64), g[name + '_E_x'])      # quantised W: exact
+        h2, J2, c2 = sq.formulas.dense_graph_calculate_hamiltonian(W, dtype)
+        assert np.allclose(h2, g[name + '_h'], atol=tol(dtype) * 10) and np.allclose(J2, g[name + '_J'], atol=tol(dtype))
+        Eq = sq.formulas.dense_graph_batch_calculate_E_from_spin(g[name + '_h'], g[name + '_J'], g[name + '_c'], q, dtype)
+        assert np.allclose(Eq, want, rtol=tol(dtype), atol=tol(dtype) * 10)
+
+
+@pytest.mark.parametrize('dtype', DT)
+def test_known_answers(sq, dtype):
+    N = 10
+    W = np.ones((N, N))
+    ann = sq.dense_graph_annealer(W, sq.minimize, dtype, n_trotters=4)
+    ann.prepare()
+    ann.set_q(-np.ones(N, np.int8))
+    assert np.allclose(ann.get_E(), 0, atol=1e-5)
+    ann.set_q(np.ones(N, np.int8))
+    assert np.allclose(ann.get_E(), N * N, atol=1e-4)
+    assert all(np.array_equal(x, np.ones(N, np.int8)) for x in ann.get_x())
+    with pytest.raises(RuntimeError):        # anneal before prepare / q set (test_dense_graph_annealer.py:390-393)
+        a2 = sq.dense_graph_annealer(W, sq.minimize, dtype)
+        a2.anneal_one_step(1., 1.)
+    p = ann.get_preferences()
+    assert p['algorithm'] == 'coloring' and p['n_trotters'] == 4 and p['device'] == 'cuda'
+    assert p['precision'] == ('float' if dtype == np.float32 else 'double')
+    ann.set_preferences(algorithm='naive')   # unsupported -> default (CUDA table, test_dense_graph_annealer.py:454-482)
+    assert ann.get_preferences()['algorithm'] == 'coloring'
+    ann.set_preferences(algorithm='sa_default')
+    assert ann.get_preferences()['algorithm'] == 'sa_naive'
+
+
+@pytest.mark.parametrize('dtype', DT)
+def test_system_E_vs_golden(sq, golden_dense, dtype):
+    g = golden_dense
+    for opt, tag in ((sq.minimize, 'min'), (sq.maximize, 'max')):
+        ann = sq.dense_graph_annealer(g['Wr16'], opt, dtype, n_trotters=6)
+        ann.prepare()
+        ann.set_qset(g['Wr16_sys_%s_q' % tag])
+        assert np.allclose(ann.get_E(), g['Wr16_sys_%s_E' % tag], rtol=tol(dtype), atol=tol(dtype) * 10)
+        want = g['Wr16_sys_%s_sysE' % tag] * (1 if tag == 'min' else -1)   # C++ solvers flip once more for maximize
+        got = ann.get_system_E(0.7, 1. / 0.03)
+        assert abs(got - want) <= (2e-5 if dtype == np.float32 else 1e-10) * max(1., abs(want))
+
+
+CHAIN_CASES = [
+    # N, m, algorithm, steps
+    (10, 4, 'coloring', 6),
+    (40, 20, 'coloring', 3),
+    (33, 7, 'coloring', 4),        # odd ring: trotter m-1 is its own phase
+    (16, 2, 'coloring', 4),        # both neighbours are the same trotter
+    (100, 151, 'coloring', 2),     # more trotters than CTAs -> mixed T, odd m
+    (300, 296, 'coloring', 1),     # T = 2 everywhere, every CTA has remote neighbours
+    (1000, 32, 'coloring', 1),
+    (2100, 12, 'coloring', 1),     # more than one 2048-spin super-block, several chunks per row
+    (24, 1, 'sa_naive', 5),
+    (50, 9, 'sa_naive', 3),
+]
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('N,m,algo,steps', CHAIN_CASES)
+def test_exact_chain_vs_oracle(sq, oracle, N, m, algo, steps, dtype):
+    """The kernel and the oracle (philox mode) must produce identical spins step by step."""
+    W = quantized_symmetric_W(N, 1000 + N, dtype)
+    for seed in range(5, 25):
+        ref = oracle.DenseGraphAnnealer(W, 0, dtype, n_trotters=m, algorithm=algo, rng='philox')
+        ref.seed(seed); ref.prepare(); ref.randomize_spin()
+        ann = sq.dense_graph_annealer(W, sq.minimize, dtype, n_trotters=m, algorithm=algo)
+        ann.seed(seed); ann.prepare(); ann.randomize_spin()
+        assert np.array_equal(ann.get_spins(), ref.get_q()), 'randomize_spin stream differs'
+        G, beta = (3.0, 1. / 0.3) if algo == 'coloring' else (2.0, 1.0)
+        traj_ok = True
+        for s in range(steps):
+            ref.anneal_one_step(G, beta)
+            ann.anneal_one_step(G, beta)
+            G *= 0.7
+            if ref.stats()[1] > 0:
+                traj_ok = False      # an accept test sat on the rounding edge: try the next seed
+                break
+            got, want = ann.get_spins(), ref.get_q()
+            assert np.array_equal(got, want), 'step %d: %d spins differ (seed %d)' % (s, int((got != want).sum()), seed)
+        if traj_ok:
+            assert ref.stats()[0] > 0          # the chain did move
+            assert ann.get_stats()['accepted'] == ref.stats()[0]
+            assert np.allclose(ann.get_E(), ref.get_E(), rtol=tol(dtype), atol=tol(dtype) * 10)
+            return
+    pytest.fail('no seed without a borderline accept test')
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('algo,m', [('coloring', 4), ('default', 4), ('sa_naive', 1), ('sa_naive', 4), ('coloring', 1)])
+def test_reaches_ground_state(sq, algo, m, dtype):
+    # sqaodpy/tests/test_dense_graph_annealer.py:180-260
+    N = 10
+    for sign, opt, want in ((1.0, sq.minimize, 0.0), (-1.0, sq.minimize, -N * N), (1.0, sq.maximize, N * N)):
+        ann = sq.dense_graph_annealer(sign * np.ones((N, N)), opt, dtype, n_trotters=m, algorithm=algo)
+        ann.seed(11); ann.prepare(); ann.randomize_spin()
+        sa = not sq.algorithm.is_sqa(ann.get_preferences()['algorithm'])
+        G, Gfin, beta = (10.0, 0.02, 1.0) if sa else (5.0, 0.02, 1. / 0.03)
+        tau = (Gfin / G) ** 0.01
+        for _ in range(100):
+            ann.anneal_one_step(G, beta)
+            G *= tau
+        ann.make_solution()
+        E = ann.get_E()
+        assert (E.min() if opt is sq.minimize else E.max()) == want
+
+
+def test_set_q_get_q_roundtrip(sq):
+    # sqaodc/tests/CUDADenseGraphAnnealerTest.cpp:191-247
+    N, m = 40, 20
+    rng = np.random.default_rng(0)
+    ann = sq.dense_graph_annealer(quantized_symmetric_W(N, 3), sq.minimize, np.float32, n_trotters=m)
+    ann.prepare()
+    q = (2 * rng.integers(0, 2, N) - 1).astype(np.int8)
+    ann.set_q(q)
+    assert all(np.array_equal(v, q) for v in ann.get_q()) and len(ann.get_q()) == m
+    qs = (2 * rng.integers(0, 2, (m + 3, N)) - 1).astype(np.int8)
+    ann.set_qset(qs)                                   # also changes the number of trotters
+    assert ann.get_preferences()['n_trotters'] == m + 3
+    assert np.array_equal(np.stack(ann.get_q()), qs)
+    assert np.array_equal(np.stack(ann.get_x()), (qs + 1) // 2)

@@ -81,7 +81,7 @@ private:
     int ldJ_, ldq_;
     real c_;
     unsigned long long seed_, step_, randomizeCount_, launchCount_;
-    int grid_, chunkElems_, chunksPerRow_, stages_, nw64_, nWindows_;
+    int grid_, chunkElems_, chunksPerRow_, stages_, nw64_, nWindows_, K_;
     size_t smemBytes_;
     HostVector E_;
     std::vector<signed char> hq_;

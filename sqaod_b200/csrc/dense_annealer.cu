@@ -35,7 +35,7 @@
 
 namespace sqb {
 
-enum { SW_K = 16, SW_DOT_WARPS = 8, SW_THREADS = (SW_DOT_WARPS + 1) * 32, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4 };
+enum { SW_MAX_K = 16, SW_DOT_WARPS = 8, SW_THREADS = (SW_DOT_WARPS + 1) * 32, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4 };
 
 template <class real> struct SweepParams {
     const real *J;
@@ -44,7 +44,7 @@ template <class real> struct SweepParams {
     int ldJ, ldq, N, m;
     unsigned long long seed, step;
     real twoDivM, coef, beta;
-    int chunkElems, chunksPerRow, stages, nw64;
+    int chunkElems, chunksPerRow, stages, nw64, K;
     unsigned long long *acceptFlags; /* [m][SW_FLAG_RING] */
     unsigned long long *snapFlags;   /* [m] */
     unsigned long long *snapBits;    /* [m][SW_SNAP_SLOTS][nw64] */
@@ -55,22 +55,22 @@ template <class real> struct SweepParams {
 /* shared-memory carve-up, identical on host and device */
 template <class real> struct SweepSmem {
     size_t ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, us, hs, xn, conf, total;
-    __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages) {
+    __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K) {
         size_t o = 0;
         ring = o; o += (size_t)SW_DOT_WARPS * stages * chunkElems * sizeof(real);
         bars = o; o += (size_t)SW_DOT_WARPS * stages * 8;
         qcur = o; o += (size_t)T * nw64 * 8;
         qsnap = o; o += (size_t)T * nw64 * 8;
         nbsnap = o; o += (size_t)2 * nw64 * 8;
-        dots = o; o += (size_t)2 * T * SW_K * sizeof(real);
+        dots = o; o += (size_t)2 * T * K * sizeof(real);
         o = (o + 15) & ~(size_t)15;
-        cross = o; o += (size_t)2 * T * SW_K * 32 * sizeof(real);
-        xs = o; o += (size_t)3 * T * SW_K * 4;
+        cross = o; o += (size_t)2 * T * K * (2 * K) * sizeof(real);
+        xs = o; o += (size_t)3 * T * K * 4;
         o = (o + 15) & ~(size_t)15;
-        us = o; o += (size_t)3 * T * SW_K * sizeof(real);
-        hs = o; o += (size_t)3 * T * SW_K * sizeof(real);
-        xn = o; o += (size_t)2 * 3 * SW_K * 4;
-        conf = o; o += (size_t)2 * SW_K * 4;
+        us = o; o += (size_t)3 * T * K * sizeof(real);
+        hs = o; o += (size_t)3 * T * K * sizeof(real);
+        xn = o; o += (size_t)2 * 3 * K * 4;
+        conf = o; o += (size_t)2 * K * 4;
         total = (o + 127) & ~(size_t)127;
     }
 };
@@ -103,11 +103,11 @@ __device__ __forceinline__ int sweepPhase(int y, int m) { /* 0: even, 1: trotter
     return ((m & 1) && y == m - 1) ? 1 : 0;
 }
 
-template <class real, bool SQA>
+template <class real, bool SQA, int K>
 __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<real> P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int N = P.N, m = P.m, K = SW_K;
+    const int N = P.N, m = P.m;
     const int G = gridDim.x, cta = blockIdx.x;
     const int baseT = m / G, remT = m % G;
     const int T = baseT + (cta < remT ? 1 : 0);
@@ -117,14 +117,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
     const int CH = P.chunkElems, CPR = P.chunksPerRow, S = P.stages, NW = P.nw64;
     const int GPC = CH >> 7;
 
-    const SweepSmem<real> L(maxT, NW, CH, S);
+    const SweepSmem<real> L(maxT, NW, CH, S, K);
     real *ring = reinterpret_cast<real *>(smem + L.ring);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
     unsigned long long *qcur = reinterpret_cast<unsigned long long *>(smem + L.qcur);
     unsigned long long *qsnap = reinterpret_cast<unsigned long long *>(smem + L.qsnap);
     unsigned long long *nbsnap = reinterpret_cast<unsigned long long *>(smem + L.nbsnap);
     real *dots = reinterpret_cast<real *>(smem + L.dots);    /* [2][maxT][K] */
-    real *cross = reinterpret_cast<real *>(smem + L.cross);  /* [2][maxT][K][32] */
+    real *cross = reinterpret_cast<real *>(smem + L.cross);  /* [2][maxT][K][2K] */
     int *xs = reinterpret_cast<int *>(smem + L.xs);          /* [3][maxT][K] */
     real *us = reinterpret_cast<real *>(smem + L.us);
     real *hs = reinterpret_cast<real *>(smem + L.hs);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
             /* column whose J[x][col] this lane must pick up: lane j < K -> round j of window w-1, else round j-K of w */
             int px = -1;
             if (lane < K) { if (w > 0) px = xs[(((w - 1) % 3) * maxT + t) * K + lane]; }
-            else if (lane - K < rl) px = xs[((w % 3) * maxT + t) * K + (lane - K)];
+            else if (lane < 2 * K && lane - K < rl) px = xs[((w % 3) * maxT + t) * K + (lane - K)];
             real crossv = real(0);
             real a0 = real(0), a1 = real(0), a2 = real(0), a3 = real(0);
             const unsigned long long *qrow = qsnap + (size_t)t * NW;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
             }
             real s = warpSum((a0 + a1) + (a2 + a3));
             if (lane == 0) dots[(buf * maxT + t) * K + rl] = s;
-            cross[((buf * maxT + t) * K + rl) * 32 + lane] = crossv;
+            if (lane < 2 * K) cross[((buf * maxT + t) * K + rl) * (2 * K) + lane] = crossv;
         }
     };
 
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
         if (mask) {
             const int yn = side ? yRight : yLeft;
             const int nbPhase = sweepPhase(yn, m);
-            uint32_t vis = (w > 0 ? 0xffffu : 0u) | (((1u << rl) - 1u) << K) | ((nbPhase < myPhase) ? (1u << (K + rl)) : 0u);
+            uint32_t vis = (w > 0 ? ((1u << K) - 1u) : 0u) | (((1u << rl) - 1u) << K) | ((nbPhase < myPhase) ? (1u << (K + rl)) : 0u);
             mask &= vis;
             while (mask) {
                 int j = __ffs(mask) - 1;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
                 for (int side = 0; side < 2; ++side) {
                     int nbx = -1;
                     if (lane < K) { if (w > 0) nbx = xn[(side * 3 + (w - 1) % 3) * K + lane]; }
-                    else if (lane - K < Kw) nbx = xn[(side * 3 + slot) * K + (lane - K)];
+                    else if (lane < 2 * K && lane - K < Kw) nbx = xn[(side * 3 + slot) * K + (lane - K)];
                     const int tEdge = side ? T - 1 : 0;
                     for (int rl = 0; rl < Kw; ++rl) {
                         int xe = xs[(slot * maxT + tEdge) * K + rl];
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
                         const real qyx = up ? real(1) : real(-1);
                         /* repair the snapshot dot product with every flip accepted since the snapshot */
                         real sum = dots[(buf * maxT + lane) * K + rl];
-                        const real *cr = cross + ((buf * maxT + lane) * K + rl) * 32;
+                        const real *cr = cross + ((buf * maxT + lane) * K + rl) * (2 * K);
                         uint32_t ev = accP | ((accC & ((1u << rl) - 1u)) << K);
                         const uint32_t sg = sgnP | (sgnC << K);
                         while (ev) {
@@ -475,6 +475,14 @@ long long ringSpinDot(const B200Device &dev, const signed char *q, int ldq, int 
     return h;
 }
 
+template <class real> static const void *sweepKernelFor(bool sqa, int K) {
+    switch (K) {
+    case 16: return sqa ? (const void *)denseSweepKernel<real, true, 16> : (const void *)denseSweepKernel<real, false, 16>;
+    case 8: return sqa ? (const void *)denseSweepKernel<real, true, 8> : (const void *)denseSweepKernel<real, false, 8>;
+    default: return sqa ? (const void *)denseSweepKernel<real, true, 4> : (const void *)denseSweepKernel<real, false, 4>;
+    }
+}
+
 /* =====================================================================================
  * host class
  * ===================================================================================== */
@@ -593,27 +601,32 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     const int nw64 = packedWords64(N_);
     int chunkElems = std::min((int)ldJ_, (int)(8192 / sizeof(real)));
     int stages = 3;
+    int K = SW_MAX_K; /* look-ahead window; shrinks when many trotters share a CTA (tables grow with T K^2) */
     for (;;) {
-        SweepSmem<real> L(maxT, nw64, chunkElems, stages);
+        SweepSmem<real> L(maxT, nw64, chunkElems, stages, K);
         if (L.total <= dev_->smemPerBlockOptin()) break;
-        if (stages > 2) --stages;
+        if (K > 4 && (size_t)2 * maxT * K * 2 * K * sizeof(real) > (size_t)48 * 1024) K >>= 1;
+        else if (stages > 2) --stages;
+        else if (chunkElems > 512) chunkElems >>= 1;
+        else if (K > 4) K >>= 1;
         else if (chunkElems > 128) chunkElems >>= 1;
         else sqb_throwError("problem too large for the sweep kernel's shared memory (N=%d, m=%d).", N_, m_);
     }
+    K_ = K;
     grid_ = G;
     chunkElems_ = chunkElems;
     chunksPerRow_ = (ldJ_ + chunkElems - 1) / chunkElems;
     stages_ = stages;
     nw64_ = nw64;
-    smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages).total;
-    nWindows_ = (N_ + SW_K - 1) / SW_K;
+    smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages, K).total;
+    nWindows_ = (N_ + K - 1) / K;
     dAcceptFlags_.alloc(dev_, (size_t)m_ * SW_FLAG_RING);
     dSnapFlags_.alloc(dev_, m_);
     dSnapBits_.alloc(dev_, (size_t)m_ * SW_SNAP_SLOTS * nw64);
     dStats_.alloc(dev_, 2);
     launchCount_ = 0;
-    CUDA_CHECK(cudaFuncSetAttribute(denseSweepKernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
-    CUDA_CHECK(cudaFuncSetAttribute(denseSweepKernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
+    CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(true, K_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
+    CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(false, K_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
     xlist_.clear();
     qlist_.clear();
     setState(solPrepared);
@@ -743,13 +756,13 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
         P.coef = real(0.);
         P.beta = real(1.) / G;
     }
-    P.chunkElems = chunkElems_; P.chunksPerRow = chunksPerRow_; P.stages = stages_; P.nw64 = nw64_;
+    P.chunkElems = chunkElems_; P.chunksPerRow = chunksPerRow_; P.stages = stages_; P.nw64 = nw64_; P.K = K_;
     P.acceptFlags = dAcceptFlags_.p; P.snapFlags = dSnapFlags_.p; P.snapBits = dSnapBits_.p;
     P.roundBase = (launchCount_ + 1ull) * (unsigned long long)(N_ + SW_FLAG_RING);
     P.snapBase = (launchCount_ + 1ull) * (unsigned long long)(nWindows_ + 2);
     P.stats = dStats_.p;
     void *args[] = {&P};
-    const void *fn = sqa ? (const void *)denseSweepKernel<real, true> : (const void *)denseSweepKernel<real, false>;
+    const void *fn = sweepKernelFor<real>(sqa, K_);
     dev_->makeCurrent();
     CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid_), dim3(SW_THREADS), args, smemBytes_, dev_->stream()));
     ++dev_->launchCount;

@@ -1,0 +1,107 @@
+"""GPU parity tests of the bipartite-graph annealer (through the C ABI)."""
+import numpy as np
+import pytest
+from conftest import quantized_bipartite
+
+pytestmark = pytest.mark.gpu
+DT = [np.float32, np.float64]
+
+
+def tol(dtype):
+    return 1e-5 if dtype == np.float32 else 1e-12
+
+
+@pytest.fixture(scope='module')
+def sq():
+    import sqaod_b200
+    return sqaod_b200
+
+
+@pytest.mark.parametrize('dtype', DT)
+def test_formulas_and_energy_vs_golden(sq, golden_bipartite, dtype):
+    g = golden_bipartite
+    b0, b1, W = g['b0'], g['b1'], g['W']
+    f = sq.formulas
+    h0, h1, J, c = f.bipartite_graph_calculate_hamiltonian(b0, b1, W, dtype)
+    for a, b in ((h0, g['h0']), (h1, g['h1']), (J, g['J']), (c, g['c'])):
+        assert np.allclose(a, b, atol=tol(dtype) * 10)
+    assert np.array_equal(f.bipartite_graph_batch_calculate_E_2d(b0, b1, W, g['x0_2d'], g['x1'], dtype).astype(np.float64), g['E_2d'])
+    assert np.array_equal(f.bipartite_graph_batch_calculate_E(b0, b1, W, g['bx0'], g['bx1'], dtype).astype(np.float64), g['E_x'])
+    assert f.bipartite_graph_calculate_E(b0, b1, W, g['bx0'][0], g['bx1'][0], dtype) == g['E_x0']
+    Eq = f.bipartite_graph_batch_calculate_E_from_spin(g['h0'], g['h1'], g['J'], g['c'], 2 * g['bx0'] - 1, 2 * g['bx1'] - 1, dtype)
+    assert np.allclose(Eq, g['E_q'], rtol=tol(dtype), atol=tol(dtype) * 10)
+    for opt, tag in ((sq.minimize, 'min'), (sq.maximize, 'max')):
+        ann = sq.bipartite_graph_annealer(b0, b1, W, opt, dtype, n_trotters=6)
+        ann.prepare()
+        q0, q1 = g['sys_%s_q0' % tag], g['sys_%s_q1' % tag]
+        ann.set_qset([(q0[i], q1[i]) for i in range(6)])
+        assert np.allclose(ann.get_E(), g['sys_%s_E' % tag], rtol=tol(dtype), atol=tol(dtype) * 10)
+        want = g['sys_%s_sysE' % tag] * (1 if tag == 'min' else -1)
+        assert abs(ann.get_system_E(0.7, 1. / 0.03) - want) <= (2e-5 if dtype == np.float32 else 1e-10) * max(1., abs(want))
+        got = ann.get_q()
+        assert all(np.array_equal(got[i][0], q0[i]) and np.array_equal(got[i][1], q1[i]) for i in range(6))
+        hh0, hh1, JJ, cc = ann.get_hamiltonian()
+        s = 1 if tag == 'min' else -1
+        assert np.allclose(hh0, s * g['h0'], atol=tol(dtype) * 10) and np.allclose(JJ, s * g['J'], atol=tol(dtype) * 10)
+
+
+@pytest.mark.parametrize('dtype', DT)
+def test_known_answers(sq, dtype):
+    # test_bipartite_graph_annealer.py:170-182: W = 1, q = +1 -> E == N0*N1 + N0 + N1
+    N0, N1 = 6, 5
+    ann = sq.bipartite_graph_annealer(np.ones(N0), np.ones(N1), np.ones((N1, N0)), sq.minimize, dtype, n_trotters=3)
+    ann.prepare()
+    ann.set_q((np.ones(N0, np.int8), np.ones(N1, np.int8)))
+    assert np.allclose(ann.get_E(), N0 * N1 + N0 + N1, atol=1e-4)
+    p = ann.get_preferences()
+    assert p['algorithm'] == 'coloring' and p['n_trotters'] == 3 and p['device'] == 'cuda'
+    ann.set_preferences(algorithm='sa_naive')
+    assert ann.get_preferences()['algorithm'] == 'sa_coloring'
+    assert ann.get_problem_size() == (N0, N1)
+
+
+CASES = [(5, 4, 6, 'coloring', 4), (40, 24, 7, 'coloring', 3), (100, 130, 32, 'coloring', 2), (70, 33, 2, 'coloring', 3),
+         (16, 20, 1, 'sa_coloring', 4), (64, 48, 9, 'sa_coloring', 3)]
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('N0,N1,m,algo,steps', CASES)
+def test_exact_chain_vs_oracle(sq, oracle, N0, N1, m, algo, steps, dtype):
+    """same Philox stream -> identical spins after every step (quantised inputs keep the contraction exact)."""
+    b0, b1, W = quantized_bipartite(N0, N1, 500 + N0, dtype)
+    seed = 9
+    ref = oracle.BipartiteGraphAnnealer(b0, b1, W, 0, dtype, n_trotters=m, algorithm=algo, rng='philox')
+    ref.seed(seed); ref.prepare(); ref.randomize_spin()
+    ann = sq.bipartite_graph_annealer(b0, b1, W, sq.minimize, dtype, n_trotters=m, algorithm=algo)
+    ann.seed(seed); ann.prepare(); ann.randomize_spin()
+    G, beta = (3.0, 1. / 0.3) if algo == 'coloring' else (2.0, 1.0)
+    for s in range(steps + 1):
+        q = ann.get_q()
+        got0, got1 = np.stack([p[0] for p in q]), np.stack([p[1] for p in q])
+        want0, want1 = ref.get_q()
+        nbad = int((got0 != want0).sum() + (got1 != want1).sum())
+        # an accept test can sit on a rounding edge (exp, fma contraction); allow a handful of such spins per step
+        assert nbad <= (0 if s == 0 else 2 * s), 'step %d: %d spins differ' % (s, nbad)
+        if nbad:
+            ann.set_qset(list(zip(want0, want1)))      # re-synchronise and keep checking the following steps
+        if s < steps:
+            ref.anneal_one_step(G, beta); ann.anneal_one_step(G, beta)
+            G *= 0.7
+    assert np.allclose(ann.get_E(), ref.get_E(), rtol=tol(dtype), atol=tol(dtype) * 10)
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('algo,m', [('coloring', 4), ('sa_coloring', 4), ('default', 1)])
+def test_reaches_ground_state(sq, algo, m, dtype):
+    N0, N1 = 6, 5
+    ann = sq.bipartite_graph_annealer(-np.ones(N0), -np.ones(N1), -np.ones((N1, N0)), sq.minimize, dtype, n_trotters=m, algorithm=algo)
+    ann.seed(3); ann.prepare(); ann.randomize_spin()
+    sa = not sq.algorithm.is_sqa(ann.get_preferences()['algorithm'])
+    G, beta = (10.0, 1.0) if sa else (5.0, 1. / 0.03)
+    for _ in range(100):
+        ann.anneal_one_step(G, beta)
+        G *= (0.02 / 5.0) ** 0.01
+    ann.make_solution()
+    assert ann.get_E().min() == -(N0 * N1 + N0 + N1)
+    x = ann.get_x()
+    assert len(x) == m

@@ -160,8 +160,9 @@ def main():
     import sqaod_b200 as sq
     dev = sq.Device(local_rank)
     sq.set_active_device(dev)
-    stream = torch.cuda.current_stream()
-    dev.set_stream(stream.cuda_stream)          # our kernels run on torch's current stream, so torch events time them
+    stream = torch.cuda.Stream()                # a real (non-default) stream shared by torch events and our kernels
+    torch.cuda.set_stream(stream)
+    dev.set_stream(stream.cuda_stream)
 
     N, m = args.N, args.m
     W = make_problem(N)

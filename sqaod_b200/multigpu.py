@@ -1,0 +1,104 @@
+"""Multi-GPU drivers for the parts of the path that shard.  One process per GPU, torch.distributed for
+the plumbing (NCCL on the GPUs; the host-side logic also runs under gloo for the CPU tests).
+
+  * brute-force search: the x range is cut into `world` contiguous slabs, every rank searches its slab with the
+    single-GPU searcher, then ONE exchange step: all_reduce(MIN) on the minimum (exact: min is order independent),
+    all_gather of the argmin lists of the ranks that hold the global minimum, merge ascending, cap.  The result does
+    not depend on the number of ranks.
+  * annealing replicas: independent seeds per rank, no data-path collective; an optional final MIN-reduce of the best
+    energy.
+"""
+import numpy as np
+
+
+def shard_range(x_max, rank, world):
+    """contiguous slab [begin, end) of [0, x_max) for `rank`; slabs differ by at most one element."""
+    base, rem = divmod(int(x_max), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def _device_for(group_backend):
+    import torch
+    return torch.device('cuda', torch.cuda.current_device()) if group_backend == 'nccl' else torch.device('cpu')
+
+
+def merge_bf_results(local_Emin, local_xs, cap, minimize=True, group=None):
+    """The exchange step of the sharded search.  local_Emin: this rank's best energy (user sign), local_xs: its packed
+    argmins (uint64).  Returns (Emin, merged ascending packed list capped at `cap`), identical on every rank."""
+    import torch
+    dist = _dist()
+    if not (dist.is_available() and dist.is_initialized()):
+        xs = np.sort(np.asarray(local_xs, np.uint64))[:cap]
+        return float(local_Emin), xs
+    world = dist.get_world_size(group)
+    dev = _device_for(dist.get_backend(group))
+    key = float(local_Emin) if minimize else -float(local_Emin)
+    e = torch.tensor([key], dtype=torch.float64, device=dev)
+    dist.all_reduce(e, op=dist.ReduceOp.MIN, group=group)
+    gmin = float(e.item())
+    mine = np.sort(np.asarray(local_xs, np.uint64))[:cap] if key == gmin else np.empty(0, np.uint64)
+    n = torch.tensor([len(mine)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    width = max(max(counts), 1)
+    buf = torch.zeros(width, dtype=torch.int64, device=dev)
+    if len(mine):
+        buf[:len(mine)] = torch.from_numpy(mine.view(np.int64)).to(dev)
+    gathered = [torch.zeros(width, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, buf, group=group)
+    parts = [g[:c].cpu().numpy().view(np.uint64) for g, c in zip(gathered, counts) if c]
+    xs = np.sort(np.concatenate(parts)) if parts else np.empty(0, np.uint64)
+    return (gmin if minimize else -gmin), xs[:cap]
+
+
+def sharded_dense_bf_search(W, optimize, dtype, cap=1 << 16, group=None, local_search=None, **prefs):
+    """Exhaustive search over x in [0, 2^N) split across the ranks of `group`.
+
+    local_search(W, optimize, dtype, x_begin, x_end) -> (Emin, packed xs) may be injected (the CPU tests inject the
+    oracle); by default the B200 searcher is used.  Returns (Emin, list of int8 bit vectors, ascending)."""
+    dist = _dist()
+    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    N = W.shape[0]
+    begin, end = shard_range(1 << N, rank, world)
+    minimize = int(optimize) == 0
+    if local_search is None:
+        from . import solvers
+
+        def local_search(W_, opt_, dtype_, b, e):
+            s = solvers.dense_graph_bf_searcher(W_, opt_, dtype_, **prefs)
+            s.set_range(b, e)
+            s.prepare()
+            while not s.search_range()[0]:
+                pass
+            return s.get_Emin(), s.get_packed_x()
+    if end > begin:
+        Emin, xs = local_search(W, optimize, dtype, begin, end)
+    else:
+        Emin, xs = (np.inf if minimize else -np.inf), np.empty(0, np.uint64)
+    Emin, xs = merge_bf_results(Emin, xs, cap, minimize, group)
+    from .common import create_bitset_sequence
+    return np.dtype(dtype).type(Emin), create_bitset_sequence([int(v) for v in xs], N)
+
+
+def replica_seed(base_seed, rank, replica):
+    """seed of replica `replica` on rank `rank` (replica r of the whole job has seed base + r)."""
+    return int(base_seed) + int(replica)
+
+
+def best_energy_over_ranks(local_best, minimize=True, group=None):
+    import torch
+    dist = _dist()
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(local_best)
+    dev = _device_for(dist.get_backend(group))
+    t = torch.tensor([float(local_best)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN if minimize else dist.ReduceOp.MAX, group=group)
+    return float(t.item())

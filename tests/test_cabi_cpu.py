@@ -1,0 +1,85 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/sqaod_b200.h declares, keeps the
+reference's host-side semantics (preferences, state machine errors) and fails loudly without a device.  No compute."""
+import ctypes as C
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from sqaod_b200 import _lib
+    return _lib
+
+
+def test_every_declared_symbol_is_exported(lib):
+    syms = lib.declared_symbols()
+    assert len(syms) > 90
+    missing = [s for s in syms if not hasattr(lib.lib, s)]
+    assert missing == []
+
+
+def test_version_symbol_of_the_reference(lib):
+    # sqaodpy/sqaod/common/envcheck.py:77-99 requires ver >= 10002
+    ver, cuda = C.c_int(0), C.c_int(0)
+    lib.lib.sqaodc_cuda_version(C.byref(ver), C.byref(cuda))
+    assert ver.value >= 10002 and cuda.value >= 12000
+    assert lib.lib.sqb_version() >= 100
+
+
+@pytest.mark.parametrize('dt', [0, 1])
+def test_host_side_preferences_and_errors(lib, dt):
+    L = lib.lib
+    h = C.c_void_p()
+    assert L.sqb_dg_annealer_new(C.byref(h), dt) == 0
+    buf = C.create_string_buffer(256)
+    assert L.sqb_dg_annealer_get_preferences(h, buf, 256, dt) == 0
+    prefs = dict(kv.split('=') for kv in buf.value.decode().split(';'))
+    assert prefs['algorithm'] == 'coloring' and prefs['device'] == 'cuda'
+    assert prefs['precision'] == ('float' if dt == 0 else 'double')
+    # algorithm fallbacks of the CUDA solver (test_dense_graph_annealer.py:454-482)
+    for asked, got in (('naive', 'coloring'), ('sa_default', 'sa_naive'), ('sa_coloring', 'sa_naive'), ('default', 'coloring')):
+        assert L.sqb_dg_annealer_set_preference(h, b'algorithm', asked.encode(), 0, dt) == 0
+        L.sqb_dg_annealer_get_preferences(h, buf, 256, dt)
+        assert ('algorithm=' + got) in buf.value.decode()
+    assert L.sqb_dg_annealer_set_preference(h, b'n_trotters', None, 12, dt) == 0
+    L.sqb_dg_annealer_get_preferences(h, buf, 256, dt)
+    assert 'n_trotters=12' in buf.value.decode()
+    assert L.sqb_dg_annealer_set_preference(h, b'n_trotters', None, 0, dt) != 0           # must be positive
+    assert b'positive' in L.sqb_last_error()
+    assert L.sqb_dg_annealer_set_preference(h, b'no_such_pref', None, 1, dt) != 0
+    # no device assigned: problem upload must fail, not fall back
+    W = np.eye(4, dtype=np.float32 if dt == 0 else np.float64)
+    assert L.sqb_dg_annealer_set_qubo(h, W.ctypes.data_as(C.c_void_p), 4, 4, 0, dt) != 0
+    assert b'Device not set' in L.sqb_last_error()
+    assert L.sqb_dg_annealer_prepare(h, dt) != 0 and b'Problem is not set' in L.sqb_last_error()
+    assert L.sqb_dg_annealer_anneal_one_step(h, C.c_double(1.), C.c_double(1.), dt) != 0
+    assert L.sqb_dg_annealer_delete(h, dt) == 0
+    # brute-force searcher: tile sizes are rounded up to multiples of 256 (Solver.cpp:205)
+    s = C.c_void_p()
+    assert L.sqb_dg_bf_searcher_new(C.byref(s), dt) == 0
+    assert L.sqb_dg_bf_searcher_set_preference(s, b'tile_size', None, 1000, dt) == 0
+    L.sqb_dg_bf_searcher_get_preferences(s, buf, 256, dt)
+    assert 'tile_size=1024' in buf.value.decode() and 'algorithm=brute_force_search' in buf.value.decode()
+    assert L.sqb_dg_bf_searcher_delete(s, dt) == 0
+    assert L.sqb_dg_annealer_new(C.byref(h), 7) != 0 and b'dtype' in L.sqb_last_error()
+
+
+def test_fails_loudly_without_a_gpu(lib):
+    import sqaod_b200 as sq
+    if sq.is_cuda_available():
+        pytest.skip('a CUDA device is present')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        sq.dense_graph_annealer(np.eye(4), sq.minimize, np.float32)
+
+
+def test_python_helpers_match_the_reference():
+    import sqaod_b200 as sq
+    W = np.triu(np.arange(16, dtype=np.float64).reshape(4, 4))
+    S = sq.symmetrize(W)
+    assert np.array_equal(S, S.T) and np.array_equal(np.diag(S), np.diag(W))
+    with pytest.raises(RuntimeError):
+        sq.symmetrize(np.arange(16, dtype=np.float64).reshape(4, 4))
+    x = sq.create_bitset_sequence([5, 2], 4)                 # MSB first (Common.cpp:78-93)
+    assert x.tolist() == [[0, 1, 0, 1], [0, 0, 1, 0]]
+    assert int(sq.minimize) == 0 and int(sq.maximize) == 1
+    assert sq.algorithm.is_sqa('coloring') and not sq.algorithm.is_sqa('sa_naive')

@@ -67,6 +67,7 @@ public:
     void setSpinsRaw(const signed char *q, int m);
     void getSpinsRaw(signed char *q) const;
     void getStats(unsigned long long *accepted, unsigned long long *waits) const;
+    void getBarrierStats(unsigned long long *dot, unsigned long long *chain) const { *dot = lastBarrierWaitDot_; *chain = lastBarrierWaitChain_; }
     int numTrotters() const { return m_; }
     B200Device *device() const { return dev_; }
 
@@ -83,6 +84,7 @@ private:
     unsigned long long seed_, step_, randomizeCount_, launchCount_;
     int grid_, chunkElems_, chunksPerRow_, stages_, nw64_, nWindows_, K_;
     size_t smemBytes_;
+    mutable unsigned long long lastBarrierWaitDot_ = 0, lastBarrierWaitChain_ = 0;
     HostVector E_;
     std::vector<signed char> hq_;
     sq::BitSetArray xlist_, qlist_;

@@ -202,6 +202,11 @@ int sqb_dg_annealer_anneal_one_step(sqb_handle ann, double G, double beta, int d
 int sqb_dg_annealer_get_stats(sqb_handle ann, unsigned long long *accepted, unsigned long long *waits, int dtype) {
     SQB_TRY DISPATCH(dtype, DGAX(real)->getStats(accepted, waits)) SQB_CATCH
 }
+int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, unsigned long long *chain, int dtype) {
+    SQB_TRY
+    DISPATCH(dtype, { unsigned long long a, w; DGAX(real)->getStats(&a, &w); DGAX(real)->getBarrierStats(dot, chain); })
+    SQB_CATCH
+}
 int sqb_dg_annealer_get_spins(sqb_handle ann, signed char *q, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getSpinsRaw(q)) SQB_CATCH }
 
 /* ---------------- bipartite-graph annealer ---------------- */

@@ -35,7 +35,7 @@
 
 namespace sqb {
 
-enum { SW_MAX_K = 16, SW_DOT_WARPS = 8, SW_THREADS = (SW_DOT_WARPS + 1) * 32, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4 };
+enum { SW_MAX_K = 16, SW_DOT_WARPS = 16, SW_THREADS = (SW_DOT_WARPS + 1) * 32, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4 };
 
 template <class real> struct SweepParams {
     const real *J;
@@ -49,7 +49,7 @@ template <class real> struct SweepParams {
     unsigned long long *snapFlags;   /* [m] */
     unsigned long long *snapBits;    /* [m][SW_SNAP_SLOTS][nw64] */
     unsigned long long roundBase, snapBase;
-    unsigned long long *stats;       /* [0] accepted flips, [1] remote waits */
+    unsigned long long *stats;       /* [0] accepted flips, [1] remote wait polls, [2]/[3] barrier-wait cycles of dot warp 0 / chain warp */
 };
 
 /* shared-memory carve-up, identical on host and device */
@@ -243,9 +243,18 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
                 const int g0 = c * GPC;
                 unsigned long long bits = qrow[((g0 >> 4) << 5) + lane] >> ((g0 & 15) << 2);
                 const real *src = buf_ + lane * 4;
+                if (groups == 16) {
+                    const uint32_t blo = (uint32_t)bits, bhi = (uint32_t)(bits >> 32);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (i < groups) accumGroup(src + i * 128, (uint32_t)(bits >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+                    for (int i = 0; i < 8; ++i) accumGroup(src + i * 128, (blo >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) accumGroup(src + (i + 8) * 128, (bhi >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+                } else if (groups == 8) {
+                    const uint32_t blo = (uint32_t)bits;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) accumGroup(src + i * 128, (blo >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+                } else {
+                    for (int i = 0; i < groups; ++i) accumGroup(src + i * 128, (uint32_t)(bits >> (4 * i)) & 0xfu, a0, a1, a2, a3);
                 }
                 if (px >= c0 && px < c0 + (groups << 7)) crossv = buf_[px - c0];
                 __syncwarp();
@@ -271,6 +280,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
     const bool lLocal = (yl >= y0 && yl < y0 + T), rLocal = (yr >= y0 && yr < y0 + T);
     uint32_t accP = 0, sgnP = 0, accC = 0, sgnC = 0;
     unsigned long long nAccepted = 0, nWaits = 0;
+    long long barrierWait = 0; /* cycles this warp's lane 0 spent at the end-of-window barrier */
 
     /* spin of a trotter owned by another CTA: published snapshot, corrected by the accept bits of the neighbour's
      * attempts that hit the same spin index since the snapshot */
@@ -288,8 +298,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
                 long long rr = (long long)w * K + (j - K); /* j < K: previous window */
                 const unsigned long long want = P.roundBase + (unsigned long long)rr + 1ull;
                 const unsigned long long *f = P.acceptFlags + (size_t)yn * SW_FLAG_RING + (rr % SW_FLAG_RING);
-                unsigned long long got = ldAcquire(f);
-                while ((got >> 1) != want) { ++nWaits; __nanosleep(20); got = ldAcquire(f); }
+                /* the flag word carries its own payload (tag, accept bit): relaxed accesses are enough */
+                unsigned long long got = ldRelaxed(f);
+                while ((got >> 1) != want) { ++nWaits; __nanosleep(20); got = ldRelaxed(f); }
                 if (got & 1ull) v = -v;
             }
         }
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
                         }
                         if (remote && (lane == 0 || lane == T - 1)) {
                             const unsigned long long rr = (unsigned long long)w * K + rl;
-                            stRelease(P.acceptFlags + (size_t)y * SW_FLAG_RING + (rr % SW_FLAG_RING),
+                            stRelaxed(P.acceptFlags + (size_t)y * SW_FLAG_RING + (rr % SW_FLAG_RING),
                                       ((P.roundBase + rr + 1ull) << 1) | (acc ? 1ull : 0ull));
                         }
                     }
@@ -383,7 +394,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
             }
             accP = accC; sgnP = sgnC; accC = 0; sgnC = 0;
         }
-        __syncthreads();
+        {
+            const long long t0 = clock64();
+            __syncthreads();
+            if (lane == 0 && (warp == 0 || chainWarp)) barrierWait += clock64() - t0;
+        }
         /* new snapshot S_{w+1}; publish the edge trotters for the neighbouring CTAs */
         for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
         if (remote && w + 1 < nW) {
@@ -422,8 +437,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
         if (lane == 0) {
             atomicAdd(P.stats, nAccepted);
             atomicAdd(P.stats + 1, nWaits);
+            atomicAdd(P.stats + 3, (unsigned long long)barrierWait); /* chain warp waiting for the dot warps */
         }
     }
+    if (warp == 0 && lane == 0 && P.stats) atomicAdd(P.stats + 2, (unsigned long long)barrierWait); /* dot warp 0 waiting */
 }
 
 /* ---------------- small element-wise kernels ---------------- */
@@ -599,7 +616,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     const int G = std::min(dev_->numSMs(), (int)m_);
     const int maxT = (m_ + G - 1) / G;
     const int nw64 = packedWords64(N_);
-    int chunkElems = std::min((int)ldJ_, (int)(8192 / sizeof(real)));
+    int chunkElems = std::min((int)ldJ_, (int)(4096 / sizeof(real)));
     int stages = 3;
     int K = SW_MAX_K; /* look-ahead window; shrinks when many trotters share a CTA (tables grow with T K^2) */
     for (;;) {
@@ -623,7 +640,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     dAcceptFlags_.alloc(dev_, (size_t)m_ * SW_FLAG_RING);
     dSnapFlags_.alloc(dev_, m_);
     dSnapBits_.alloc(dev_, (size_t)m_ * SW_SNAP_SLOTS * nw64);
-    dStats_.alloc(dev_, 2);
+    dStats_.alloc(dev_, 4);
     launchCount_ = 0;
     CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(true, K_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
     CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(false, K_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
@@ -771,13 +788,15 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
 }
 
 template <class real> void B200DenseGraphAnnealer<real>::getStats(unsigned long long *accepted, unsigned long long *waits) const {
-    unsigned long long h[2] = {0, 0};
+    unsigned long long h[4] = {0, 0, 0, 0};
     if (dStats_.p) {
         dev_->d2h(h, dStats_.p, sizeof(h));
         dev_->synchronize();
     }
     *accepted = h[0];
     *waits = h[1];
+    lastBarrierWaitDot_ = h[2];
+    lastBarrierWaitChain_ = h[3];
 }
 
 template class B200DenseGraphAnnealer<float>;

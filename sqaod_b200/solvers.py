@@ -171,7 +171,9 @@ class DenseGraphAnnealer(_SolverBase):
     def get_stats(self):
         a = C.c_ulonglong(0); w = C.c_ulonglong(0)
         _lib.check(L.sqb_dg_annealer_get_stats(self._cobj, C.byref(a), C.byref(w), self._dt))
-        return {'accepted': a.value, 'flag_waits': w.value}
+        d = C.c_ulonglong(0); c = C.c_ulonglong(0)
+        _lib.check(L.sqb_dg_annealer_get_barrier_cycles(self._cobj, C.byref(d), C.byref(c), self._dt))
+        return {'accepted': a.value, 'flag_waits': w.value, 'barrier_cycles_dot': d.value, 'barrier_cycles_chain': c.value}
 
 
 def dense_graph_annealer(W=None, optimize=minimize, dtype=np.float64, device=None, **prefs):

@@ -194,7 +194,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
     /* ---------------- dot warps: per-warp TMA ring state ---------------- */
     /* task = (window w, id = rl * T + t); warp d owns ids d, d + 8, ... of every window */
     int iw = 0, iid = warp, ic = 0, ix = 0; /* issue cursor (lane 0) */
-    unsigned issued = 0, consumed = 0;
+    int iStage = 0;                         /* ring slot the next issue goes to */
+    int cStage = 0;                         /* ring slot the next consume reads, and its mbarrier phase parity */
+    uint32_t cParity = 0;
     bool issueDone = false;
     uint64_t *myBars = bars + warp * S;
     real *myRing = ring + (size_t)warp * S * CH;
@@ -211,12 +213,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
             Philox4 p = sqbPhilox(P.seed, P.step, DOM_DENSE_SWEEP, (uint32_t)(iw * K + rl), (uint32_t)(y0 + t));
             ix = (int)(p.w[0] % (uint32_t)N);
         }
-        int stage = issued % S;
-        int elems = min(CH, P.ldJ - ic * CH);
-        uint32_t bytes = (uint32_t)(elems * sizeof(real));
-        mbarArriveExpectTx(&myBars[stage], bytes);
-        tmaLoad1D(myRing + (size_t)stage * CH, P.J + (size_t)ix * P.ldJ + (size_t)ic * CH, bytes, &myBars[stage]);
-        ++issued;
+        const int elems = min(CH, P.ldJ - ic * CH);
+        const uint32_t bytes = (uint32_t)(elems * sizeof(real));
+        mbarArriveExpectTx(&myBars[iStage], bytes);
+        tmaLoad1D(myRing + (size_t)iStage * CH, P.J + (size_t)ix * P.ldJ + (size_t)ic * CH, bytes, &myBars[iStage]);
+        if (++iStage == S) iStage = 0;
         if (++ic == CPR) { ic = 0; iid += SW_DOT_WARPS; }
     };
     if (warp < SW_DOT_WARPS && lane == 0)
@@ -235,9 +236,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
             real a0 = real(0), a1 = real(0), a2 = real(0), a3 = real(0);
             const unsigned long long *qrow = qsnap + (size_t)t * NW;
             for (int c = 0; c < CPR; ++c) {
-                const int stage = consumed % S;
-                mbarWait(&myBars[stage], (consumed / S) & 1);
-                const real *buf_ = myRing + (size_t)stage * CH;
+                mbarWait(&myBars[cStage], cParity);
+                const real *buf_ = myRing + (size_t)cStage * CH;
                 const int c0 = c * CH;
                 const int groups = min(GPC, (P.ldJ - c0) >> 7);
                 const int g0 = c * GPC;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
                 if (px >= c0 && px < c0 + (groups << 7)) crossv = buf_[px - c0];
                 __syncwarp();
                 if (lane == 0) issueNext();
-                ++consumed;
+                if (++cStage == S) { cStage = 0; cParity ^= 1u; }
             }
             real s = warpSum((a0 + a1) + (a2 + a3));
             if (lane == 0) dots[(buf * maxT + t) * K + rl] = s;
@@ -279,6 +279,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
     const int yl = (y == 0) ? m - 1 : y - 1, yr = (y == m - 1) ? 0 : y + 1;
     const bool lLocal = (yl >= y0 && yl < y0 + T), rLocal = (yr >= y0 && yr < y0 + T);
     uint32_t accP = 0, sgnP = 0, accC = 0, sgnC = 0;
+    /* rows the chain reads for this lane: its own, and its neighbours' (current state when the neighbour lives in this
+     * CTA, else the published snapshot of side 0 / 1) */
+    unsigned long long *myRow = qcur + (size_t)(lane < T ? lane : 0) * NW;
+    const unsigned long long *leftRow = lLocal ? qcur + (size_t)(yl - y0) * NW : nbsnap;
+    const unsigned long long *rightRow = rLocal ? qcur + (size_t)(yr - y0) * NW : nbsnap + NW;
+    const bool publishes = remote && active && (lane == 0 || lane == T - 1);
+    unsigned long long *myFlags = P.acceptFlags + (size_t)(active ? y : 0) * SW_FLAG_RING;
     unsigned long long nAccepted = 0, nWaits = 0;
     long long barrierWait = 0; /* cycles this warp's lane 0 spent at the end-of-window barrier */
 
@@ -352,41 +359,49 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
                         const int x = xs[o];
                         int w64, bit;
                         spinBitPos(x, w64, bit);
-                        unsigned long long *word = qcur + (size_t)lane * NW + w64;
-                        const bool up = ((*word >> bit) & 1ull) != 0;
+                        unsigned long long *word = myRow + w64;
+                        /* independent shared-memory reads first: own word, both neighbours' words, dot, h, u */
+                        const unsigned long long wv = *word, lv = leftRow[w64], rv = rightRow[w64];
+                        real sum = dots[(buf * maxT + lane) * K + rl];
+                        const real hx = hs[o], ux = us[o];
+                        const uint32_t cmL = lLocal ? 0u : conf[rl], cmR = rLocal ? 0u : conf[K + rl];
+                        const bool up = ((wv >> bit) & 1ull) != 0;
                         const real qyx = up ? real(1) : real(-1);
                         /* repair the snapshot dot product with every flip accepted since the snapshot */
-                        real sum = dots[(buf * maxT + lane) * K + rl];
-                        const real *cr = cross + ((buf * maxT + lane) * K + rl) * (2 * K);
                         uint32_t ev = accP | ((accC & ((1u << rl) - 1u)) << K);
-                        const uint32_t sg = sgnP | (sgnC << K);
-                        while (ev) {
-                            int j = __ffs(ev) - 1;
-                            ev &= ev - 1;
-                            real qold = ((sg >> j) & 1u) ? real(1) : real(-1);
-                            sum += real(-2) * qold * cr[j];
+                        if (ev) {
+                            const real *cr = cross + ((buf * maxT + lane) * K + rl) * (2 * K);
+                            const uint32_t sg = sgnP | (sgnC << K);
+                            do {
+                                int j = __ffs(ev) - 1;
+                                ev &= ev - 1;
+                                real qold = ((sg >> j) & 1u) ? real(1) : real(-1);
+                                sum += real(-2) * qold * cr[j];
+                            } while (ev);
                         }
                         real dE;
                         if (SQA) {
-                            int ql = lLocal ? spinAt(qcur + (size_t)(yl - y0) * NW, x) : remoteSpin(0, x, w, rl);
-                            int qr = rLocal ? spinAt(qcur + (size_t)(yr - y0) * NW, x) : remoteSpin(1, x, w, rl);
-                            dE = P.twoDivM * qyx * (hs[o] + real(2) * sum);
+                            int ql = ((lv >> bit) & 1ull) ? 1 : -1, qr = ((rv >> bit) & 1ull) ? 1 : -1;
+                            if (cmL | cmR) { /* rare: a neighbour owned by another CTA attempted this very spin */
+                                if (cmL) ql = remoteSpin(0, x, w, rl);
+                                if (cmR) qr = remoteSpin(1, x, w, rl);
+                            }
+                            dE = P.twoDivM * qyx * (hx + real(2) * sum);
                             dE -= qyx * real(ql + qr) * P.coef;
                         } else {
-                            dE = real(2) * qyx * (hs[o] + real(2) * sum);
+                            dE = real(2) * qyx * (hx + real(2) * sum);
                         }
                         const real thr = (dE < real(0)) ? real(1) : expReal<real>(-dE * P.beta);
-                        const bool acc = thr > us[o];
+                        const bool acc = thr > ux;
                         if (acc) {
-                            *word ^= (1ull << bit);
+                            *word = wv ^ (1ull << bit);
                             accC |= 1u << rl;
                             if (up) sgnC |= 1u << rl;
                             ++nAccepted;
                         }
-                        if (remote && (lane == 0 || lane == T - 1)) {
+                        if (publishes) {
                             const unsigned long long rr = (unsigned long long)w * K + rl;
-                            stRelaxed(P.acceptFlags + (size_t)y * SW_FLAG_RING + (rr % SW_FLAG_RING),
-                                      ((P.roundBase + rr + 1ull) << 1) | (acc ? 1ull : 0ull));
+                            stRelaxed(myFlags + (rr % SW_FLAG_RING), ((P.roundBase + rr + 1ull) << 1) | (acc ? 1ull : 0ull));
                         }
                     }
                     __syncwarp();

@@ -1,6 +1,7 @@
 /* b200_solvers.hpp -- concrete solver classes of the B200 back end (internal header). */
 #pragma once
 #include "device.hpp"
+#include "tc_gemm.hpp"
 #include <vector>
 
 namespace sqb {
@@ -73,12 +74,15 @@ public:
 
 private:
     void uploadProblem(const real *h, const real *J, int strideJ);
+    void prepareTensorCoreOperand();
     void syncBits();
 
     B200Device *dev_;
     DevBuf<real> dJ_, dh_, dE_;
     DevBuf<signed char> dq_;
     DevBuf<unsigned long long> dAcceptFlags_, dSnapFlags_, dSnapBits_, dStats_;
+    TcOperand tcJ_;
+    TcWorkspace tcWs_;
     int ldJ_, ldq_;
     real c_;
     unsigned long long seed_, step_, randomizeCount_, launchCount_;

@@ -17,6 +17,7 @@
 #include "philox.cuh"
 #include "b200_solvers.hpp"
 #include <math.h>
+#include <type_traits>
 #include <time.h>
 #include <algorithm>
 
@@ -176,6 +177,14 @@ public:
         transposeMatKernel<real><<<grid, dim3(32, 32), 0, dev_->stream()>>>(dJT_.p, ldJT_, dJ_.p, ldJ_, N1_, N0_);
         CUDA_CHECK(cudaGetLastError());
         ++dev_->launchCount;
+        /* fp32: bf16 hi/mid/lo splits of J and J^T for the tcgen05 contraction (energy_tc.cu) */
+        tcJ_.ready = tcJT_.ready = false;
+        if constexpr (std::is_same<real, float>::value) {
+            if (tcEnabled()) {
+                tcPrepareOperand(*dev_, tcJ_, dJ_.p, ldJ_, N1_, N0_);
+                tcPrepareOperand(*dev_, tcJT_, dJT_.p, ldJT_, N0_, N1_);
+            }
+        }
     }
     void setQUBO(const HostVector &b0, const HostVector &b1, const HostMatrix &W, sq::OptimizeMethod om = sq::optMinimize) {
         sqb_throwErrorIf(W.cols != b0.size || W.rows != b1.size, "%s, shape mismatch between b0, b1 and W.", __func__);
@@ -331,7 +340,15 @@ private:
         this->throwErrorIfQNotSet();
         const real sign = (om_ == sq::optMaximize) ? real(-1) : real(1);
         /* E = -c - h0.q0 - h1.q1 - q1^T J q0 */
-        devBatchedEnergy<real>(*dev_, dE_.p, dJ_.p, ldJ_, N1_, N0_, dq0_.p, ldq0_, dq1_.p, ldq1_, dh1_.p, dh0_.p, m_, -sign, -sign * c_);
+        bool done = false;
+        if constexpr (std::is_same<real, float>::value) {
+            if (tcJ_.ready && tcEnabled()) {
+                tcBatchedEnergy(*dev_, dE_.p, tcJ_, dq0_.p, ldq0_, dq1_.p, ldq1_, dh1_.p, dh0_.p, m_, -sign, -sign * c_, tcWs_);
+                done = true;
+            }
+        }
+        if (!done)
+            devBatchedEnergy<real>(*dev_, dE_.p, dJ_.p, ldJ_, N1_, N0_, dq0_.p, ldq0_, dq1_.p, ldq1_, dh1_.p, dh0_.p, m_, -sign, -sign * c_);
         dev_->d2h(E_.data, dE_.p, sizeof(real) * m_);
         dev_->synchronize();
         this->setState(Base::solEAvailable);
@@ -345,7 +362,15 @@ private:
         const int ldJe = side ? ldJ_ : ldJT_;
         const real *h = side ? dh1_.p : dh0_.p;
         const unsigned dom = side ? DOM_BG_SIDE1 : DOM_BG_SIDE0;
-        devSpinGemm<real>(*dev_, ddE_.p, ldc_, Je, ldJe, qF, ldqF, m_, NA, NF);
+        bool done = false;
+        if constexpr (std::is_same<real, float>::value) {
+            const TcOperand &op = side ? tcJ_ : tcJT_;
+            if (op.ready && tcEnabled()) {
+                tcSpinGemm(*dev_, ddE_.p, ldc_, op, qF, ldqF, m_, tcWs_);
+                done = true;
+            }
+        }
+        if (!done) devSpinGemm<real>(*dev_, ddE_.p, ldc_, Je, ldJe, qF, ldqF, m_, NA, NF);
         cudaStream_t st = dev_->stream();
         const int bx = 128;
         if (!sqa) {
@@ -396,6 +421,8 @@ private:
     HostVector E_;
     std::vector<signed char> hq0_, hq1_;
     sq::BitSetPairArray xPairs_, qPairs_;
+    TcOperand tcJ_, tcJT_;
+    TcWorkspace tcWs_;
 };
 
 } // namespace sqb

@@ -30,6 +30,7 @@
 #include "philox.cuh"
 #include "b200_solvers.hpp"
 #include <math.h>
+#include <type_traits>
 #include <time.h>
 #include <algorithm>
 
@@ -558,7 +559,16 @@ template <class real> void B200DenseGraphAnnealer<real>::uploadProblem(const rea
     dh_.alloc(dev_, N_);
     dev_->h2d2D(dJ_.p, sizeof(real) * ldJ_, J, sizeof(real) * strideJ, sizeof(real) * N_, N_);
     dev_->h2d(dh_.p, h, sizeof(real) * N_);
+    prepareTensorCoreOperand();
     dev_->synchronize();
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::prepareTensorCoreOperand() {
+    /* fp32 only: J split into bf16 hi/mid/lo once per problem for the tcgen05 energy GEMM (energy_tc.cu) */
+    tcJ_.ready = false;
+    if constexpr (std::is_same<real, float>::value) {
+        if (tcEnabled()) tcPrepareOperand(*dev_, tcJ_, dJ_.p, ldJ_, N_, N_);
+    }
 }
 
 template <class real> void B200DenseGraphAnnealer<real>::setQUBO(const HostMatrix &W, sq::OptimizeMethod om) {
@@ -578,6 +588,7 @@ template <class real> void B200DenseGraphAnnealer<real>::setQUBO(const HostMatri
     dc.alloc(dev_, 1);
     dev_->h2d2D(dW.p, sizeof(real) * ldJ_, W.data, sizeof(real) * W.stride, sizeof(real) * N_, N_);
     devDenseHamiltonian<real>(*dev_, dh_.p, dJ_.p, ldJ_, dc.p, dW.p, ldJ_, N_, om == sq::optMaximize ? real(-1) : real(1));
+    prepareTensorCoreOperand();
     dev_->d2h(&c_, dc.p, sizeof(real));
     dev_->synchronize();
     setState(solProblemSet);
@@ -745,7 +756,14 @@ template <class real> void B200DenseGraphAnnealer<real>::calculate_E() {
     throwErrorIfQNotSet();
     /* E_y = -c - h.q_y - q_y^T J q_y, sign-flipped for maximize (CUDADenseGraphAnnealer.cu:260-272) */
     const real sign = (om_ == sq::optMaximize) ? real(-1) : real(1);
-    devBatchedEnergy<real>(*dev_, dE_.p, dJ_.p, ldJ_, N_, N_, dq_.p, ldq_, dq_.p, ldq_, dh_.p, NULL, m_, -sign, -sign * c_);
+    bool done = false;
+    if constexpr (std::is_same<real, float>::value) {
+        if (tcJ_.ready && tcEnabled()) {
+            tcBatchedEnergy(*dev_, dE_.p, tcJ_, dq_.p, ldq_, dq_.p, ldq_, dh_.p, NULL, m_, -sign, -sign * c_, tcWs_);
+            done = true;
+        }
+    }
+    if (!done) devBatchedEnergy<real>(*dev_, dE_.p, dJ_.p, ldJ_, N_, N_, dq_.p, ldq_, dq_.p, ldq_, dh_.p, NULL, m_, -sign, -sign * c_);
     dev_->d2h(E_.data, dE_.p, sizeof(real) * m_);
     dev_->synchronize();
     setState(solEAvailable);

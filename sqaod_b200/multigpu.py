@@ -102,3 +102,38 @@ def best_energy_over_ranks(local_best, minimize=True, group=None):
     t = torch.tensor([float(local_best)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN if minimize else dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def anneal_replicas(W, n_replicas, schedule, beta, dtype=np.float32, n_trotters=None, base_seed=0, optimize=0, group=None,
+                    algorithm='coloring'):
+    """Independent annealing replicas of ONE problem, sharded over the ranks.
+
+    Replica r of the whole job has seed base_seed + r and runs on rank r // ceil(n_replicas / world); no data-path
+    collective.  `schedule` is the list of G (kT for SA) values, one anneal_one_step each.  Returns
+    (best energy over all ranks, this rank's per-replica best energies, this rank's best replica id, its best spins)."""
+    from . import solvers
+    dist = _dist()
+    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    begin, end = shard_range(n_replicas, rank, world)
+    minimize = int(optimize) == 0
+    opt = solvers.minimize if minimize else solvers.maximize
+    prefs = {'algorithm': algorithm}
+    if n_trotters is not None:
+        prefs['n_trotters'] = n_trotters
+    ann = solvers.dense_graph_annealer(W, opt, dtype, **prefs)   # J is uploaded once per rank and reused by its replicas
+    best = np.full(max(end - begin, 0), np.inf if minimize else -np.inf)
+    best_q, best_id = None, -1
+    for k, r in enumerate(range(begin, end)):
+        ann.seed(replica_seed(base_seed, rank, r))
+        ann.prepare()
+        ann.randomize_spin()
+        for G in schedule:
+            ann.anneal_one_step(G, beta)
+        E = ann.get_E()
+        i = int(np.argmin(E) if minimize else np.argmax(E))
+        best[k] = E[i]
+        if best_id < 0 or (E[i] < best[best_id - begin] if minimize else E[i] > best[best_id - begin]):
+            best_id, best_q = r, ann.get_spins()[i].copy()
+    local_best = (best.min() if minimize else best.max()) if len(best) else (np.inf if minimize else -np.inf)
+    return best_energy_over_ranks(local_best, minimize, group), best, best_id, best_q

@@ -84,6 +84,15 @@ int sqb_dg_annealer_get_spins(sqb_handle ann, signed char *q, int dtype);
 /* SM cycles lane 0 of dot warp 0 / of the chain warp spent at the end-of-window barrier, summed over CTAs (profiling aid) */
 int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, unsigned long long *chain, int dtype);
 
+/* ring sharding over several GPUs (no reference counterpart): the solver anneals trotters
+ * [rank*m/world, (rank+1)*m/world) of ONE ring of m trotters; J and h are replicated.  Call order: set_qubo,
+ * ring_configure, prepare, ring_export -> exchange the 64-byte handles -> ring_attach(left, right), set/randomize spins,
+ * ring_push_halos, then anneal_one_step (which ends with a halo push over NVLink). */
+int sqb_dg_annealer_ring_configure(sqb_handle ann, int rank, int world, int m_global, int dtype);
+int sqb_dg_annealer_ring_export(sqb_handle ann, unsigned char *handle64, int dtype);
+int sqb_dg_annealer_ring_attach(sqb_handle ann, const unsigned char *left_handle64, const unsigned char *right_handle64, int dtype);
+int sqb_dg_annealer_ring_push_halos(sqb_handle ann, int dtype);
+
 /* ---- bipartite-graph annealer: pyglue/annealer.inc ---- */
 int sqb_bg_annealer_new(sqb_handle *ann, int dtype);
 int sqb_bg_annealer_delete(sqb_handle ann, int dtype);

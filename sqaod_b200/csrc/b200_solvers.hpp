@@ -24,7 +24,7 @@ void devBipartiteEnergy2D(const B200Device &dev, real *d_E, int ldE, const real 
                           int N0, int N1, const signed char *d_x0, int ldx0, int n0, const signed char *d_x1, int ldx1, int n1);
 
 void launchRandomizeSpin(const B200Device &dev, signed char *q, int ldq, int N, int m, unsigned long long seed,
-                         unsigned long long count, unsigned domain);
+                         unsigned long long count, unsigned domain, int yOff = 0);
 long long ringSpinDot(const B200Device &dev, const signed char *q, int ldq, int N, int m);
 
 /* extras of the dense brute-force searcher reachable through the C ABI (sharded search) */
@@ -70,6 +70,11 @@ public:
     void getStats(unsigned long long *accepted, unsigned long long *waits) const;
     void getBarrierStats(unsigned long long *dot, unsigned long long *chain) const { *dot = lastBarrierWaitDot_; *chain = lastBarrierWaitChain_; }
     int numTrotters() const { return m_; }
+    /* ring sharding over several GPUs: this solver anneals trotters [rank*m/world, (rank+1)*m/world) of one ring */
+    void ringConfigure(int rank, int world, int mGlobal);
+    void ringExport(unsigned char handle[64]) const;
+    void ringAttach(const unsigned char left[64], const unsigned char right[64]);
+    void ringPushHalos();
     B200Device *device() const { return dev_; }
 
 private:
@@ -80,7 +85,15 @@ private:
     B200Device *dev_;
     DevBuf<real> dJ_, dh_, dE_;
     DevBuf<signed char> dq_;
-    DevBuf<unsigned long long> dAcceptFlags_, dSnapFlags_, dSnapBits_, dStats_;
+    DevBuf<unsigned long long> dStats_;
+    void *handoff_;            /* accept flags, snapshots, halo rows (HandoffLayout in dense_annealer.cu) */
+    bool handoffIpc_;
+    void *peerBase_[2];        /* the left / right peer's hand-off block, opened through CUDA IPC */
+    int ringRank_, ringWorld_, mRing_, yOff_;
+    unsigned long long ringEpoch_;
+    void allocHandoff();
+    void freeHandoff();
+    void closePeer(int side);
     TcOperand tcJ_;
     TcWorkspace tcWs_;
     int ldJ_, ldq_;

@@ -209,6 +209,15 @@ int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, 
 }
 int sqb_dg_annealer_get_spins(sqb_handle ann, signed char *q, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getSpinsRaw(q)) SQB_CATCH }
 
+int sqb_dg_annealer_ring_configure(sqb_handle ann, int rank, int world, int m_global, int dtype) {
+    SQB_TRY DISPATCH(dtype, DGAX(real)->ringConfigure(rank, world, m_global)) SQB_CATCH
+}
+int sqb_dg_annealer_ring_export(sqb_handle ann, unsigned char *handle64, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->ringExport(handle64)) SQB_CATCH }
+int sqb_dg_annealer_ring_attach(sqb_handle ann, const unsigned char *left, const unsigned char *right, int dtype) {
+    SQB_TRY DISPATCH(dtype, DGAX(real)->ringAttach(left, right)) SQB_CATCH
+}
+int sqb_dg_annealer_ring_push_halos(sqb_handle ann, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->ringPushHalos()) SQB_CATCH }
+
 /* ---------------- bipartite-graph annealer ---------------- */
 #define BGA(real) as<sqc::BipartiteGraphAnnealer<real> >(ann)
 

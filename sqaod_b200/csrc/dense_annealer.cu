@@ -46,9 +46,17 @@ template <class real> struct SweepParams {
     unsigned long long seed, step;
     real twoDivM, coef, beta;
     int chunkElems, chunksPerRow, stages, nw64, K;
-    unsigned long long *acceptFlags; /* [m][SW_FLAG_RING] */
-    unsigned long long *snapFlags;   /* [m] */
-    unsigned long long *snapBits;    /* [m][SW_SNAP_SLOTS][nw64] */
+    /* hand-off arrays have m + 2 slots: local trotter l -> slot l; slot m / m + 1 = the trotter left of local 0 / right of
+     * local m-1 when it lives on another GPU (ring sharding); the owning GPU mirrors its publications into them */
+    unsigned long long *acceptFlags; /* [m+2][SW_FLAG_RING] */
+    unsigned long long *snapFlags;   /* [m+2] */
+    unsigned long long *snapBits;    /* [m+2][SW_SNAP_SLOTS][nw64] */
+    /* ring sharding: this launch owns trotters yOff .. yOff+m-1 of a ring of mRing; mRing == m: unsharded */
+    int mRing, yOff;
+    const signed char *haloQ[2];         /* spins of the left / right foreign neighbour at step start (pushed by the peers) */
+    const unsigned long long *stepFlags; /* [2]: epoch of the last halo push received from the left / right peer */
+    unsigned long long stepEpoch;
+    unsigned long long *peerFlags[2], *peerSnapFlags[2], *peerSnapBits[2]; /* the peers' arrays (NVLink P2P), or NULL */
     unsigned long long roundBase, snapBase;
     unsigned long long *stats;       /* [0] accepted flips, [1] remote wait polls, [2]/[3] barrier-wait cycles of dot warp 0 / chain warp */
 };
@@ -132,10 +140,22 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
     int *xn = reinterpret_cast<int *>(smem + L.xn);          /* [2 sides][3][K] */
     uint32_t *conf = reinterpret_cast<uint32_t *>(smem + L.conf); /* [2][K] */
 
-    /* trotters of other CTAs adjacent to this CTA's range (SQA only) */
-    const int yLeft = (y0 == 0) ? m - 1 : y0 - 1;
-    const int yRight = (y0 + T >= m) ? 0 : y0 + T;
-    const bool remote = SQA && (G > 1);
+    /* ring topology: local index l <-> global trotter (yOff + l) mod mRing */
+    const int mRing = P.mRing, yOff = P.yOff;
+    const bool ringSharded = (mRing != m);
+    auto gOf = [&](int l) { int g = yOff + l; return g >= mRing ? g - mRing : g; };
+    auto slotOf = [&](int g) { /* hand-off slot of global trotter g: local index, or m / m+1 for the foreign neighbours */
+        int d = g - yOff;
+        if (d < 0) d += mRing;
+        if (d < m) return d;
+        return (d == mRing - 1) ? m : m + 1;
+    };
+    /* trotters of other CTAs (or GPUs) adjacent to this CTA's range (SQA only); global indices */
+    const int gFirst = gOf(y0), gLast = gOf(y0 + T - 1);
+    const int yLeft = (gFirst == 0) ? mRing - 1 : gFirst - 1;
+    const int yRight = (gLast == mRing - 1) ? 0 : gLast + 1;
+    const int slotL = slotOf(yLeft), slotR = slotOf(yRight);
+    const bool remote = SQA && (G > 1 || ringSharded);
 
     auto roundsIn = [&](int w) { return min(K, N - w * K); };
 
@@ -145,7 +165,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
         const int Kw = roundsIn(w), slot = w % 3;
         for (int idx = t0; idx < Kw * T; idx += nthr) {
             int t = idx % T, rl = idx / T;
-            Philox4 p = sqbPhilox(P.seed, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)(y0 + t));
+            Philox4 p = sqbPhilox(P.seed, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)gOf(y0 + t));
             int x = (int)(p.w[0] % (uint32_t)N);
             int o = (slot * maxT + t) * K + rl;
             xs[o] = x;
@@ -169,13 +189,26 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
         mbarInitFence();
     }
     __syncthreads();
+    if (ringSharded && remote && (slotL >= m || slotR >= m)) {
+        /* a neighbour lives on another GPU: its spins at step start arrive through the halo push of that GPU */
+        if (tid == 0) {
+            if (slotL >= m) while (ldAcquireSys(P.stepFlags + 0) < P.stepEpoch) __nanosleep(100);
+            if (slotR >= m) while (ldAcquireSys(P.stepFlags + 1) < P.stepEpoch) __nanosleep(100);
+        }
+        __syncthreads();
+    }
     {   /* pack int8 spins -> bits; 4 spins (one nibble) per thread step */
         const int n4 = (N + 3) >> 2;
         const int rows = T + (remote ? 2 : 0);
         for (int idx = tid; idx < rows * n4; idx += SW_THREADS) {
             int r = idx / n4, j = (idx % n4) << 2;
-            int y = (r < T) ? (y0 + r) : (r == T ? yLeft : yRight);
-            const signed char *src = P.q + (size_t)y * P.ldq + j;
+            const signed char *rowp;
+            if (r < T) rowp = P.q + (size_t)(y0 + r) * P.ldq;
+            else {
+                const int sl = (r == T) ? slotL : slotR;
+                rowp = (sl < m) ? P.q + (size_t)sl * P.ldq : P.haloQ[sl - m];
+            }
+            const signed char *src = rowp + j;
             unsigned nib = 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
@@ -211,7 +244,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
             skipEmptyWindows(iw, iid);
             if (iw >= nW) { issueDone = true; return; }
             int t = iid % T, rl = iid / T;
-            Philox4 p = sqbPhilox(P.seed, P.step, DOM_DENSE_SWEEP, (uint32_t)(iw * K + rl), (uint32_t)(y0 + t));
+            Philox4 p = sqbPhilox(P.seed, P.step, DOM_DENSE_SWEEP, (uint32_t)(iw * K + rl), (uint32_t)gOf(y0 + t));
             ix = (int)(p.w[0] % (uint32_t)N);
         }
         const int elems = min(CH, P.ldJ - ic * CH);
@@ -275,9 +308,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
     /* ---------------- chain warp state ---------------- */
     const bool chainWarp = (warp == SW_DOT_WARPS);
     const bool active = chainWarp && (lane < T);
-    const int y = y0 + lane;
-    const int myPhase = sweepPhase(y, m);
-    const int yl = (y == 0) ? m - 1 : y - 1, yr = (y == m - 1) ? 0 : y + 1;
+    const int y = y0 + lane;                 /* local index */
+    const int gy = gOf(lane < T ? y : y0);   /* global trotter */
+    const int myPhase = sweepPhase(gy, mRing);
+    const int yl = slotOf(gy == 0 ? mRing - 1 : gy - 1), yr = slotOf(gy == mRing - 1 ? 0 : gy + 1); /* slots of the neighbours */
     const bool lLocal = (yl >= y0 && yl < y0 + T), rLocal = (yr >= y0 && yr < y0 + T);
     uint32_t accP = 0, sgnP = 0, accC = 0, sgnC = 0;
     /* rows the chain reads for this lane: its own, and its neighbours' (current state when the neighbour lives in this
@@ -287,6 +321,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
     const unsigned long long *rightRow = rLocal ? qcur + (size_t)(yr - y0) * NW : nbsnap + NW;
     const bool publishes = remote && active && (lane == 0 || lane == T - 1);
     unsigned long long *myFlags = P.acceptFlags + (size_t)(active ? y : 0) * SW_FLAG_RING;
+    /* the first / last trotter of a sharded ring also publishes into the neighbouring GPU's arrays */
+    unsigned long long *mirror0 = (ringSharded && active && y == 0 && P.peerFlags[0]) ? P.peerFlags[0] + (size_t)(m + 1) * SW_FLAG_RING : NULL;
+    unsigned long long *mirror1 = (ringSharded && active && y == m - 1 && P.peerFlags[1]) ? P.peerFlags[1] + (size_t)m * SW_FLAG_RING : NULL;
     unsigned long long nAccepted = 0, nWaits = 0;
     long long barrierWait = 0; /* cycles this warp's lane 0 spent at the end-of-window barrier */
 
@@ -297,7 +334,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
         uint32_t mask = conf[side * K + rl];
         if (mask) {
             const int yn = side ? yRight : yLeft;
-            const int nbPhase = sweepPhase(yn, m);
+            const int nbPhase = sweepPhase(yn, mRing);
             uint32_t vis = (w > 0 ? ((1u << K) - 1u) : 0u) | (((1u << rl) - 1u) << K) | ((nbPhase < myPhase) ? (1u << (K + rl)) : 0u);
             mask &= vis;
             while (mask) {
@@ -305,10 +342,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
                 mask &= mask - 1;
                 long long rr = (long long)w * K + (j - K); /* j < K: previous window */
                 const unsigned long long want = P.roundBase + (unsigned long long)rr + 1ull;
-                const unsigned long long *f = P.acceptFlags + (size_t)yn * SW_FLAG_RING + (rr % SW_FLAG_RING);
+                const unsigned long long *f = P.acceptFlags + (size_t)(side ? slotR : slotL) * SW_FLAG_RING + (rr % SW_FLAG_RING);
                 /* the flag word carries its own payload (tag, accept bit): relaxed accesses are enough */
-                unsigned long long got = ldRelaxed(f);
-                while ((got >> 1) != want) { ++nWaits; __nanosleep(20); got = ldRelaxed(f); }
+                unsigned long long got = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f);
+                while ((got >> 1) != want) { ++nWaits; __nanosleep(20); got = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f); }
                 if (got & 1ull) v = -v;
             }
         }
@@ -324,13 +361,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
             if (remote) {
                 if (w >= 2) { /* neighbours' snapshot S_{w-1} (state before window w-1) */
                     for (int side = 0; side < 2; ++side) {
-                        const int yn = side ? yRight : yLeft;
+                        const int sl = side ? slotR : slotL;
                         if (lane == 0) {
                             const unsigned long long want = P.snapBase + (unsigned long long)(w - 1);
-                            while (ldAcquire(P.snapFlags + yn) < want) { ++nWaits; __nanosleep(50); }
+                            if (ringSharded) { while (ldAcquireSys(P.snapFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
+                            else { while (ldAcquire(P.snapFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
                         }
                         __syncwarp();
-                        const unsigned long long *src = P.snapBits + ((size_t)yn * SW_SNAP_SLOTS + ((w - 1) % SW_SNAP_SLOTS)) * NW;
+                        const unsigned long long *src = P.snapBits + ((size_t)sl * SW_SNAP_SLOTS + ((w - 1) % SW_SNAP_SLOTS)) * NW;
                         for (int i = lane; i < NW; i += 32) nbsnap[(size_t)side * NW + i] = __ldcg(src + i);
                     }
                 }
@@ -354,7 +392,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
             for (int rl = 0; rl < Kw; ++rl) {
 #pragma unroll 1
                 for (int ph = 0; ph < 3; ++ph) {
-                    if (ph == 1 && !(m & 1)) continue;
+                    if (ph == 1 && !(mRing & 1)) continue;
                     if (active && myPhase == ph) {
                         const int o = (slot * maxT + lane) * K + rl;
                         const int x = xs[o];
@@ -402,7 +440,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
                         }
                         if (publishes) {
                             const unsigned long long rr = (unsigned long long)w * K + rl;
-                            stRelaxed(myFlags + (rr % SW_FLAG_RING), ((P.roundBase + rr + 1ull) << 1) | (acc ? 1ull : 0ull));
+                            const unsigned long long fv = ((P.roundBase + rr + 1ull) << 1) | (acc ? 1ull : 0ull);
+                            stRelaxed(myFlags + (rr % SW_FLAG_RING), fv);
+                            if (mirror0) stRelaxedSys(mirror0 + (rr % SW_FLAG_RING), fv);
+                            if (mirror1) stRelaxedSys(mirror1 + (rr % SW_FLAG_RING), fv);
                         }
                     }
                     __syncwarp();
@@ -422,14 +463,25 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
             for (int i = tid; i < nEdge * NW; i += SW_THREADS) {
                 int e = i / NW, k = i % NW;
                 int t = e ? T - 1 : 0;
-                P.snapBits[((size_t)(y0 + t) * SW_SNAP_SLOTS + ((w + 1) % SW_SNAP_SLOTS)) * NW + k] = qcur[(size_t)t * NW + k];
+                const unsigned long long v = qcur[(size_t)t * NW + k];
+                const size_t off = (size_t)((w + 1) % SW_SNAP_SLOTS) * NW + k;
+                P.snapBits[(size_t)(y0 + t) * SW_SNAP_SLOTS * NW + off] = v;
+                if (ringSharded) {
+                    if (y0 + t == 0 && P.peerSnapBits[0]) P.peerSnapBits[0][(size_t)(m + 1) * SW_SNAP_SLOTS * NW + off] = v;
+                    if (y0 + t == m - 1 && P.peerSnapBits[1]) P.peerSnapBits[1][(size_t)m * SW_SNAP_SLOTS * NW + off] = v;
+                }
             }
-            __threadfence();
+            if (ringSharded) __threadfence_system(); else __threadfence();
         }
         __syncthreads();
         if (remote && w + 1 < nW && tid == 0) {
-            stRelease(P.snapFlags + y0, P.snapBase + (unsigned long long)(w + 1));
-            if (T > 1) stRelease(P.snapFlags + y0 + T - 1, P.snapBase + (unsigned long long)(w + 1));
+            const unsigned long long sv = P.snapBase + (unsigned long long)(w + 1);
+            stRelease(P.snapFlags + y0, sv);
+            if (T > 1) stRelease(P.snapFlags + y0 + T - 1, sv);
+            if (ringSharded) {
+                if (y0 == 0 && P.peerSnapFlags[0]) stReleaseSys(P.peerSnapFlags[0] + m + 1, sv);
+                if (y0 + T == m && P.peerSnapFlags[1]) stReleaseSys(P.peerSnapFlags[1] + m, sv);
+            }
         }
     }
 
@@ -461,13 +513,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
 
 /* ---------------- small element-wise kernels ---------------- */
 __global__ void randomizeSpinKernel(signed char *q, int ldq, int N, int m, unsigned long long seed,
-                                    unsigned long long count, unsigned domain) {
+                                    unsigned long long count, unsigned domain, int yOff) {
     /* one Philox call per 128 spins (reference: DeviceKernels.cu:549-572 takes the LSB of a pool word per spin) */
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     int groups = (N + 127) >> 7;
     if (g >= groups * m) return;
     int y = g / groups, grp = g % groups;
-    Philox4 p = sqbPhilox(seed, count, domain, (uint32_t)grp, (uint32_t)y);
+    Philox4 p = sqbPhilox(seed, count, domain, (uint32_t)grp, (uint32_t)(y + yOff));
     signed char *row = q + (size_t)y * ldq;
     int x0 = grp << 7;
     for (int k = 0; k < 128 && x0 + k < N; ++k) row[x0 + k] = ((p.w[(k >> 5) & 3] >> (k & 31)) & 1u) ? 1 : -1;
@@ -489,9 +541,9 @@ __global__ void ringSpinDotKernel(const signed char *q, int ldq, int N, int m, l
 }
 
 void launchRandomizeSpin(const B200Device &dev, signed char *q, int ldq, int N, int m, unsigned long long seed,
-                         unsigned long long count, unsigned domain) {
+                         unsigned long long count, unsigned domain, int yOff) {
     int groups = ((N + 127) >> 7) * m;
-    randomizeSpinKernel<<<(groups + 127) / 128, 128, 0, dev.stream()>>>(q, ldq, N, m, seed, count, domain);
+    randomizeSpinKernel<<<(groups + 127) / 128, 128, 0, dev.stream()>>>(q, ldq, N, m, seed, count, domain, yOff);
     CUDA_CHECK(cudaGetLastError());
     ++dev.launchCount;
 }
@@ -508,6 +560,19 @@ long long ringSpinDot(const B200Device &dev, const signed char *q, int ldq, int 
     return h;
 }
 
+struct HandoffLayout { /* one block per solver so that a single IPC handle exposes everything a peer writes */
+    size_t flags, snapFlags, snapBits, stepFlags, haloQ, total;
+    HandoffLayout(int m, int nw64, int ldq) {
+        size_t o = 0;
+        flags = o; o += (size_t)(m + 2) * SW_FLAG_RING * 8;
+        snapFlags = o; o += (size_t)(m + 2) * 8;
+        snapBits = o; o += (size_t)(m + 2) * SW_SNAP_SLOTS * nw64 * 8;
+        stepFlags = o; o += 16;
+        haloQ = o; o += (size_t)4 * ldq; /* [side][epoch parity][ldq] */
+        total = (o + 255) & ~(size_t)255;
+    }
+};
+
 template <class real> static const void *sweepKernelFor(bool sqa, int K) {
     switch (K) {
     case 16: return sqa ? (const void *)denseSweepKernel<real, true, 16> : (const void *)denseSweepKernel<real, false, 16>;
@@ -521,10 +586,15 @@ template <class real> static const void *sweepKernelFor(bool sqa, int K) {
  * ===================================================================================== */
 template <class real> B200DenseGraphAnnealer<real>::B200DenseGraphAnnealer()
     : dev_(NULL), ldJ_(0), ldq_(0), c_(0), seed_(0), step_(0), randomizeCount_(0), launchCount_(0), nWindows_(0) {
+    handoff_ = NULL; handoffIpc_ = false; peerBase_[0] = peerBase_[1] = NULL;
+    ringRank_ = 0; ringWorld_ = 1; mRing_ = 0; yOff_ = 0; ringEpoch_ = 0;
     m_ = -1;
     selectAlgorithm(sq::algoDefault);
 }
-template <class real> B200DenseGraphAnnealer<real>::~B200DenseGraphAnnealer() {}
+template <class real> B200DenseGraphAnnealer<real>::~B200DenseGraphAnnealer() {
+    for (int side = 0; side < 2; ++side) closePeer(side);
+    freeHandoff();
+}
 
 template <class real> void B200DenseGraphAnnealer<real>::assignDevice(sq::cuda::Device &device) {
     sqb_throwErrorIf(dev_ != NULL, "Device assigned more than once.");
@@ -663,9 +733,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     nw64_ = nw64;
     smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages, K).total;
     nWindows_ = (N_ + K - 1) / K;
-    dAcceptFlags_.alloc(dev_, (size_t)m_ * SW_FLAG_RING);
-    dSnapFlags_.alloc(dev_, m_);
-    dSnapBits_.alloc(dev_, (size_t)m_ * SW_SNAP_SLOTS * nw64);
+    allocHandoff();
     dStats_.alloc(dev_, 4);
     launchCount_ = 0;
     CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(true, K_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
@@ -677,7 +745,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
 
 template <class real> void B200DenseGraphAnnealer<real>::randomizeSpin() {
     throwErrorIfNotPrepared();
-    launchRandomizeSpin(*dev_, dq_.p, ldq_, N_, m_, seed_, randomizeCount_++, DOM_RANDOMIZE);
+    launchRandomizeSpin(*dev_, dq_.p, ldq_, N_, m_, seed_, randomizeCount_++, DOM_RANDOMIZE, ringWorld_ > 1 ? yOff_ : 0);
     setState(solQSet);
 }
 
@@ -798,8 +866,9 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
     P.seed = seed_; P.step = step_;
     const bool sqa = (algo_ == sq::algoColoring);
     if (sqa) {
-        P.twoDivM = real(2.) / real(m_);
-        P.coef = std::log(std::tanh(G * beta / m_)) / beta;
+        const int mAll = (ringWorld_ > 1) ? mRing_ : m_; /* the whole ring, also when this GPU holds a shard of it */
+        P.twoDivM = real(2.) / real(mAll);
+        P.coef = std::log(std::tanh(G * beta / mAll)) / beta;
         P.beta = beta;
     } else { /* annealOneStep(kT, _) for SA: CUDADenseGraphAnnealer.cu:585-602 */
         P.twoDivM = real(2.);
@@ -807,7 +876,23 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
         P.beta = real(1.) / G;
     }
     P.chunkElems = chunkElems_; P.chunksPerRow = chunksPerRow_; P.stages = stages_; P.nw64 = nw64_; P.K = K_;
-    P.acceptFlags = dAcceptFlags_.p; P.snapFlags = dSnapFlags_.p; P.snapBits = dSnapBits_.p;
+    HandoffLayout hl(m_, nw64_, ldq_);
+    unsigned char *hb = (unsigned char *)handoff_;
+    P.acceptFlags = (unsigned long long *)(hb + hl.flags); P.snapFlags = (unsigned long long *)(hb + hl.snapFlags);
+    P.snapBits = (unsigned long long *)(hb + hl.snapBits);
+    const bool ring = ringWorld_ > 1;
+    P.mRing = ring ? mRing_ : m_;
+    P.yOff = ring ? yOff_ : 0;
+    P.stepFlags = (const unsigned long long *)(hb + hl.stepFlags);
+    P.stepEpoch = ringEpoch_;
+    for (int side = 0; side < 2; ++side) {
+        P.haloQ[side] = (const signed char *)(hb + hl.haloQ) + (size_t)(side * 2 + (ringEpoch_ & 1)) * ldq_;
+        unsigned char *pb = ring ? (unsigned char *)peerBase_[side] : NULL;
+        P.peerFlags[side] = pb ? (unsigned long long *)(pb + hl.flags) : NULL;
+        P.peerSnapFlags[side] = pb ? (unsigned long long *)(pb + hl.snapFlags) : NULL;
+        P.peerSnapBits[side] = pb ? (unsigned long long *)(pb + hl.snapBits) : NULL;
+    }
+    if (ring) sqb_throwErrorIf(peerBase_[0] == NULL || peerBase_[1] == NULL, "ring sharding: peers not attached.");
     P.roundBase = (launchCount_ + 1ull) * (unsigned long long)(N_ + SW_FLAG_RING);
     P.snapBase = (launchCount_ + 1ull) * (unsigned long long)(nWindows_ + 2);
     P.stats = dStats_.p;
@@ -818,6 +903,98 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
     ++dev_->launchCount;
     ++launchCount_;
     ++step_;
+    if (ringWorld_ > 1) ringPushHalos(); /* per-sweep boundary exchange over NVLink */
+}
+
+/* ---------------- ring sharding over several GPUs ---------------- */
+
+template <class real> void B200DenseGraphAnnealer<real>::freeHandoff() {
+    if (handoff_ == NULL) return;
+    if (handoffIpc_) cudaFree(handoff_); else dev_->free(handoff_);
+    handoff_ = NULL;
+}
+template <class real> void B200DenseGraphAnnealer<real>::allocHandoff() {
+    freeHandoff();
+    HandoffLayout hl(m_, nw64_, ldq_);
+    handoffIpc_ = ringWorld_ > 1;
+    if (handoffIpc_) { /* plain cudaMalloc: exportable with cudaIpcGetMemHandle (pool memory is not) */
+        dev_->makeCurrent();
+        CUDA_CHECK(cudaMalloc(&handoff_, hl.total));
+        CUDA_CHECK(cudaMemsetAsync(handoff_, 0, hl.total, dev_->stream()));
+        dev_->synchronize();
+    } else
+        handoff_ = dev_->alloc(hl.total);
+    for (int side = 0; side < 2; ++side) closePeer(side);
+    ringEpoch_ = 0;
+}
+template <class real> void B200DenseGraphAnnealer<real>::closePeer(int side) {
+    if (peerBase_[side] != NULL) {
+        if (side == 1 && peerBase_[1] == peerBase_[0]) { peerBase_[1] = NULL; return; }
+        cudaIpcCloseMemHandle(peerBase_[side]);
+        if (side == 0 && peerBase_[1] == peerBase_[0]) peerBase_[1] = NULL;
+        peerBase_[side] = NULL;
+    }
+}
+template <class real> void B200DenseGraphAnnealer<real>::ringConfigure(int rank, int world, int mGlobal) {
+    sqb_throwErrorIf(world < 1 || rank < 0 || rank >= world, "ring sharding: invalid rank %d / world %d.", rank, world);
+    sqb_throwErrorIf(mGlobal % world != 0 || mGlobal / world < 2, "ring sharding: n_trotters (%d) must be a multiple of the number "
+                     "of GPUs (%d) with at least 2 trotters per GPU.", mGlobal, world);
+    ringRank_ = rank; ringWorld_ = world; mRing_ = mGlobal;
+    m_ = mGlobal / world;
+    yOff_ = rank * m_;
+    clearState(solPrepared);
+}
+template <class real> void B200DenseGraphAnnealer<real>::ringExport(unsigned char handle[64]) const {
+    throwErrorIfNotPrepared();
+    sqb_throwErrorIf(!handoffIpc_, "ring sharding is not configured.");
+    cudaIpcMemHandle_t h;
+    CUDA_CHECK(cudaIpcGetMemHandle(&h, handoff_));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+    memcpy(handle, &h, 64);
+}
+template <class real> void B200DenseGraphAnnealer<real>::ringAttach(const unsigned char left[64], const unsigned char right[64]) {
+    throwErrorIfNotPrepared();
+    sqb_throwErrorIf(!handoffIpc_, "ring sharding is not configured.");
+    dev_->makeCurrent();
+    for (int side = 0; side < 2; ++side) closePeer(side);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, left, 64);
+    CUDA_CHECK(cudaIpcOpenMemHandle(&peerBase_[0], h, cudaIpcMemLazyEnablePeerAccess));
+    if (memcmp(left, right, 64) == 0) peerBase_[1] = peerBase_[0]; /* two GPUs: both neighbours are the same peer */
+    else {
+        memcpy(&h, right, 64);
+        CUDA_CHECK(cudaIpcOpenMemHandle(&peerBase_[1], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+}
+
+__global__ void ringPushKernel(const signed char *qFirst, const signed char *qLast, signed char *dstLeftPeer, signed char *dstRightPeer,
+                               int n, unsigned long long *flagLeftPeer, unsigned long long *flagRightPeer, unsigned long long epoch) {
+    /* my first trotter is the left peer's right neighbour, my last trotter the right peer's left neighbour */
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        dstLeftPeer[i] = qFirst[i];
+        dstRightPeer[i] = qLast[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        stReleaseSys(flagLeftPeer, epoch);
+        stReleaseSys(flagRightPeer, epoch);
+    }
+}
+template <class real> void B200DenseGraphAnnealer<real>::ringPushHalos() {
+    throwErrorIfQNotSet();
+    sqb_throwErrorIf(ringWorld_ <= 1, "ring sharding is not configured.");
+    sqb_throwErrorIf(peerBase_[0] == NULL || peerBase_[1] == NULL, "ring sharding: peers not attached.");
+    HandoffLayout hl(m_, nw64_, ldq_);
+    ++ringEpoch_;
+    const size_t par = ringEpoch_ & 1;
+    unsigned char *L = (unsigned char *)peerBase_[0], *R = (unsigned char *)peerBase_[1];
+    signed char *dstL = (signed char *)(L + hl.haloQ) + (size_t)(1 * 2 + par) * ldq_;  /* left peer's RIGHT halo */
+    signed char *dstR = (signed char *)(R + hl.haloQ) + (size_t)(0 * 2 + par) * ldq_;  /* right peer's LEFT halo */
+    unsigned long long *fL = (unsigned long long *)(L + hl.stepFlags) + 1, *fR = (unsigned long long *)(R + hl.stepFlags) + 0;
+    ringPushKernel<<<1, 256, 0, dev_->stream()>>>(dq_.p, dq_.p + (size_t)(m_ - 1) * ldq_, dstL, dstR, N_, fL, fR, ringEpoch_);
+    CUDA_CHECK(cudaGetLastError());
+    ++dev_->launchCount;
 }
 
 template <class real> void B200DenseGraphAnnealer<real>::getStats(unsigned long long *accepted, unsigned long long *waits) const {

@@ -84,6 +84,24 @@ __device__ __forceinline__ unsigned long long ldRelaxed(const unsigned long long
     return v;
 }
 
+/* system scope: flags written / polled across GPUs over NVLink (ring sharding) */
+__device__ __forceinline__ void stReleaseSys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ldAcquireSys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stRelaxedSys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ldRelaxedSys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 /* ---- packed spin rows ----
  * A trotter's N spins are kept as bits (1 = +1) in 64-bit words laid out for the sweep's dot product: the row is
  * cut into groups of 128 spins; inside a group, lane l of a warp owns spins 4l..4l+3 (one 128-bit load of J);

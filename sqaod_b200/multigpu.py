@@ -137,3 +137,81 @@ def anneal_replicas(W, n_replicas, schedule, beta, dtype=np.float32, n_trotters=
             best_id, best_q = r, ann.get_spins()[i].copy()
     local_best = (best.min() if minimize else best.max()) if len(best) else (np.inf if minimize else -np.inf)
     return best_energy_over_ranks(local_best, minimize, group), best, best_id, best_q
+
+
+class RingShardedDenseAnnealer(object):
+    """ONE dense SQA instance whose trotter ring is split over the ranks of `group`.
+
+    Rank g anneals trotters [g*m/G, (g+1)*m/G); J and h are replicated.  The sweep kernel's inter-CTA hand-off (accept
+    flags + per-window snapshots of the edge trotters) is extended across GPUs by mirroring the two edge trotters'
+    publications into the neighbouring GPU's memory over NVLink (CUDA IPC peer mappings, system-scope release/acquire),
+    and every sweep ends with a push of the edge trotters' spins to the neighbours.  The chain is the same as on one
+    GPU: spins are identical to an unsharded run with the same seed (tests/ring_shard_check.py)."""
+
+    def __init__(self, W, optimize=0, dtype=np.float32, n_trotters=None, group=None):
+        from . import solvers
+        dist = _dist()
+        assert dist.is_available() and dist.is_initialized(), 'RingShardedDenseAnnealer needs torch.distributed'
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.m = int(n_trotters if n_trotters is not None else W.shape[0] // 4)
+        opt = solvers.minimize if int(optimize) == 0 else solvers.maximize
+        self.ann = solvers.dense_graph_annealer(W, opt, dtype)
+        self.ann.ring_configure(self.rank, self.world, self.m)
+        self.m_local = self.m // self.world
+        self._attached = False
+
+    def seed(self, seed):
+        self.ann.seed(seed)          # same seed on every rank: Philox is keyed by the GLOBAL trotter index
+
+    def prepare(self):
+        dist = _dist()
+        self.ann.prepare()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.ann.ring_export(), group=self.group)
+        left, right = handles[(self.rank - 1) % self.world], handles[(self.rank + 1) % self.world]
+        self.ann.ring_attach(left, right)
+        dist.barrier(group=self.group)
+        self._attached = True
+
+    def randomize_spin(self):
+        self.ann.randomize_spin()
+        self._sync_halos()
+
+    def set_qset(self, q_all):
+        """q_all: the whole m x N spin matrix (every rank passes the same array); each rank keeps its rows."""
+        q_all = np.asarray(q_all, np.int8)
+        lo = self.rank * self.m_local
+        n_before = self.ann.get_preferences()['n_trotters']
+        self.ann.set_qset(q_all[lo:lo + self.m_local])
+        assert self.ann.get_preferences()['n_trotters'] == n_before
+        self._sync_halos()
+
+    def _sync_halos(self):
+        dist = _dist()
+        self.ann._device.synchronize()
+        dist.barrier(group=self.group)   # every rank has (re)initialised its hand-off block before anyone pushes into it
+        self.ann.ring_push_halos()
+
+    def anneal_one_step(self, G, beta):
+        self.ann.anneal_one_step(G, beta)
+
+    def get_local_spins(self):
+        return self.ann.get_spins()
+
+    def get_local_E(self):
+        return self.ann.get_E()
+
+    def gather_spins(self):
+        """the whole m x N spin matrix on every rank"""
+        import torch
+        dist = _dist()
+        dev = _device_for(dist.get_backend(self.group))
+        mine = torch.from_numpy(np.ascontiguousarray(self.ann.get_spins())).to(dev)
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        return np.concatenate([p.cpu().numpy() for p in parts], axis=0)
+
+    def best_energy(self, minimize=True):
+        E = self.ann.get_E()
+        return best_energy_over_ranks(E.min() if minimize else E.max(), minimize, self.group)

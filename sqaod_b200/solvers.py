@@ -168,6 +168,22 @@ class DenseGraphAnnealer(_SolverBase):
         G, beta = self.dtype(G), self.dtype(beta)   # dense_graph_annealer_base.py:99-101
         _lib.check(L.sqb_dg_annealer_anneal_one_step(self._cobj, C.c_double(float(G)), C.c_double(float(beta)), self._dt))
 
+    # ---- ring sharding over several GPUs (sqaod_b200.multigpu.RingShardedDenseAnnealer drives these) ----
+    def ring_configure(self, rank, world, m_global):
+        _lib.check(L.sqb_dg_annealer_ring_configure(self._cobj, int(rank), int(world), int(m_global), self._dt))
+
+    def ring_export(self):
+        buf = (C.c_ubyte * 64)()
+        _lib.check(L.sqb_dg_annealer_ring_export(self._cobj, buf, self._dt))
+        return bytes(buf)
+
+    def ring_attach(self, left, right):
+        lb = (C.c_ubyte * 64).from_buffer_copy(left); rb = (C.c_ubyte * 64).from_buffer_copy(right)
+        _lib.check(L.sqb_dg_annealer_ring_attach(self._cobj, lb, rb, self._dt))
+
+    def ring_push_halos(self):
+        _lib.check(L.sqb_dg_annealer_ring_push_halos(self._cobj, self._dt))
+
     def get_stats(self):
         a = C.c_ulonglong(0); w = C.c_ulonglong(0)
         _lib.check(L.sqb_dg_annealer_get_stats(self._cobj, C.byref(a), C.byref(w), self._dt))

@@ -54,7 +54,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([s.strip() for s in out.split(',')])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -135,7 +135,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=60)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -226,6 +226,7 @@ def main():
         algo_bytes = attempts_per_step * N * 4          # one J row per attempt
         achieved = algo_bytes / (ms / args.steps * 1e-3) / 1e9
         accepted = stats1['accepted'] - stats0['accepted']
+        traffic = traffic_from_profile() if (N == N_SPINS and m == M_TROTTERS) else None
         line = {
             'metric': 'spin-flip attempts/sec (dense SQA N=8192 m=512)', 'value': value, 'unit': 'attempts/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
@@ -242,8 +243,12 @@ def main():
                     'steps': e2e_steps, 'E_min': float(np.min(E))},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic_from_profile(), 'peak_source': peak_src,
-                         'kernel': 'denseSweepKernel<float,true,16>', 'algorithmic_bytes_per_launch': algo_bytes},
+                         'traffic': traffic, 'peak_source': peak_src,
+                         'kernel': 'denseSweepKernel<float,true,16>', 'algorithmic_bytes_per_launch': algo_bytes,
+                         # the part of the algorithmic bytes that really came from HBM (ncu dram bytes per launch, profiles/):
+                         # frac > 1 on the algorithmic figure is L2 reuse of J rows, not skipped work
+                         'dram_GBps': (traffic / (ms / args.steps * 1e-3) / 1e9) if traffic else None,
+                         'dram_frac': (traffic / (ms / args.steps * 1e-3) / 1e9 / peak) if traffic else None},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -6,9 +6,11 @@
  * (CUDABipartiteGraphAnnealer.cu:392-401 -> DeviceMath.cpp:167-178, 289-309) and the batched energy
  * `xA = q . J^T` (DeviceMath.cpp:191-209).  A is split ONCE per problem into three bf16 matrices
  * A = hi + mid + lo (each residual is computed exactly in fp32, so |A - hi - mid - lo| <= 2^-27 |A|, below fp32 epsilon);
- * Q is widened to bf16 per call.  The kernel accumulates the three partial products in one fp32 TMEM accumulator:
- * products of bf16 values are exact in fp32, so the result stays within fp32 summation error of the fp32 GEMM -- and is
- * exact on the reference tests' quantised inputs.
+ * Q is widened to bf16 per call.  Each of the three partial products Q.hi^T, Q.mid^T, Q.lo^T gets its OWN fp32 TMEM
+ * accumulator (3 x 128 columns) and the epilogue adds them with round-to-nearest: tensor-core accumulation truncates, and
+ * adding the tiny mid/lo products into one large accumulator would bias every sum towards zero (measured: 1.1e-5
+ * relative on the C2 energies).  Kept apart, the hi sum needs ~21 bits and the mid/lo sums are small, so each is
+ * accumulated essentially exactly; the result is within an ulp or two of the fp32 GEMM and exact on quantised inputs.
  *
  * Structure (one CTA per 128 x 128 output tile, 192 threads):
  *   warp 0  : TMA producer -- cp.async.bulk.tensor.2d of 128x64 bf16 boxes (128B swizzle) of Q and of the A split
@@ -27,7 +29,7 @@
 
 namespace sqb {
 
-enum { TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 5, TC_THREADS = 192, TC_TMEM_COLS = 128 };
+enum { TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 5, TC_THREADS = 192, TC_TMEM_COLS = 512 /* 3 x 128 used */ };
 enum { TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2, TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 + 256 };
 
 __device__ __forceinline__ void tma2D(void *smemDst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
@@ -110,8 +112,10 @@ tcSpinGemmKernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 const unsigned char *a = smem + s * TC_STAGE_BYTES, *b = a + TC_BM * TC_BK * 2;
                 const uint64_t ad = umdesc(a), bd = umdesc(b);
 #pragma unroll
+                const int split = kb / kBlocksPerSplit; /* hi / mid / lo -> accumulator columns 0 / 128 / 256 */
+                const uint32_t first = (kb % kBlocksPerSplit) == 0 ? 0u : 1u;
                 for (int k = 0; k < TC_BK / 16; ++k) /* +32 bytes per K=16 step inside the 128-byte swizzle row */
-                    umma(tmemBase, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    umma(tmemBase + (uint32_t)(split * TC_BN), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (first | (uint32_t)k) ? 1u : 0u);
                 ummaCommit(&emptyBar[s]);
             }
             ummaCommit(tmemFullBar);
@@ -124,18 +128,26 @@ tcSpinGemmKernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 #pragma unroll 1
         for (int c = 0; c < TC_BN; c += 32) {
             uint32_t r[32];
-            const uint32_t taddr = tmemBase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float acc[32];
+#pragma unroll
+            for (int part = 2; part >= 0; --part) { /* lo, mid, hi: small terms first */
+                const uint32_t taddr = tmemBase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(part * TC_BN + c);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                      "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                      "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                      "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = (part == 2) ? __uint_as_float(r[j]) : acc[j] + __uint_as_float(r[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(acc[j]);
             if (row < m) {
                 float *dst = C + (size_t)row * ldc + n0 + c;
                 if (n0 + c + 32 <= NA && (ldc & 3) == 0) {

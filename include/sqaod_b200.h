@@ -84,6 +84,11 @@ int sqb_dg_annealer_get_spins(sqb_handle ann, signed char *q, int dtype);
 /* SM cycles lane 0 of dot warp 0 / of the chain warp spent at the end-of-window barrier, summed over CTAs (profiling aid) */
 int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, unsigned long long *chain, int dtype);
 
+/* replica batch (no reference counterpart): R independent replicas of the problem, replica r seeded
+ * seed + r, annealed side by side in one launch.  Spin and energy buffers then hold R x n_trotters rows, replica major. */
+int sqb_dg_annealer_set_num_replicas(sqb_handle ann, int n_replicas, int dtype);
+int sqb_dg_annealer_get_num_replicas(sqb_handle ann, int *n_replicas, int dtype);
+
 /* ring sharding over several GPUs (no reference counterpart): the solver anneals trotters
  * [rank*m/world, (rank+1)*m/world) of ONE ring of m trotters; J and h are replicated.  Call order: set_qubo,
  * ring_configure, prepare, ring_export -> exchange the 64-byte handles -> ring_attach(left, right), set/randomize spins,

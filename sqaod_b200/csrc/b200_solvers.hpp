@@ -24,7 +24,7 @@ void devBipartiteEnergy2D(const B200Device &dev, real *d_E, int ldE, const real 
                           int N0, int N1, const signed char *d_x0, int ldx0, int n0, const signed char *d_x1, int ldx1, int n1);
 
 void launchRandomizeSpin(const B200Device &dev, signed char *q, int ldq, int N, int m, unsigned long long seed,
-                         unsigned long long count, unsigned domain, int yOff = 0);
+                         unsigned long long count, unsigned domain, int yOff = 0, int mPerReplica = 0);
 long long ringSpinDot(const B200Device &dev, const signed char *q, int ldq, int N, int m);
 
 /* extras of the dense brute-force searcher reachable through the C ABI (sharded search) */
@@ -70,6 +70,9 @@ public:
     void getStats(unsigned long long *accepted, unsigned long long *waits) const;
     void getBarrierStats(unsigned long long *dot, unsigned long long *chain) const { *dot = lastBarrierWaitDot_; *chain = lastBarrierWaitChain_; }
     int numTrotters() const { return m_; }
+    /* replica batch: R independent replicas of the problem (seed + r) annealed side by side; spin / energy rows are [r][y] */
+    void setNumReplicas(int n);
+    int numReplicas() const { return nReplicas_; }
     /* ring sharding over several GPUs: this solver anneals trotters [rank*m/world, (rank+1)*m/world) of one ring */
     void ringConfigure(int rank, int world, int mGlobal);
     void ringExport(unsigned char handle[64]) const;
@@ -91,6 +94,7 @@ private:
     void *peerBase_[2];        /* the left / right peer's hand-off block, opened through CUDA IPC */
     int ringRank_, ringWorld_, mRing_, yOff_;
     unsigned long long ringEpoch_;
+    int nReplicas_, replicasPerLaunch_;
     void allocHandoff();
     void freeHandoff();
     void closePeer(int side);

@@ -209,6 +209,8 @@ int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, 
 }
 int sqb_dg_annealer_get_spins(sqb_handle ann, signed char *q, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getSpinsRaw(q)) SQB_CATCH }
 
+int sqb_dg_annealer_set_num_replicas(sqb_handle ann, int n, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->setNumReplicas(n)) SQB_CATCH }
+int sqb_dg_annealer_get_num_replicas(sqb_handle ann, int *n, int dtype) { SQB_TRY DISPATCH(dtype, *n = DGAX(real)->numReplicas()) SQB_CATCH }
 int sqb_dg_annealer_ring_configure(sqb_handle ann, int rank, int world, int m_global, int dtype) {
     SQB_TRY DISPATCH(dtype, DGAX(real)->ringConfigure(rank, world, m_global)) SQB_CATCH
 }

@@ -53,6 +53,9 @@ template <class real> struct SweepParams {
     unsigned long long *snapBits;    /* [m+2][SW_SNAP_SLOTS][nw64] */
     /* ring sharding: this launch owns trotters yOff .. yOff+m-1 of a ring of mRing; mRing == m: unsharded */
     int mRing, yOff;
+    /* replica batch: blockIdx.y selects replica replicaBase + blockIdx.y (seed + replica, own spins and hand-off block) */
+    int replicaBase;
+    size_t qReplicaStride, handoffReplicaStride; /* in bytes */
     const signed char *haloQ[2];         /* spins of the left / right foreign neighbour at step start (pushed by the peers) */
     const unsigned long long *stepFlags; /* [2]: epoch of the last halo push received from the left / right peer */
     unsigned long long stepEpoch;
@@ -113,8 +116,16 @@ __device__ __forceinline__ int sweepPhase(int y, int m) { /* 0: even, 1: trotter
 }
 
 template <class real, bool SQA, int K>
-__global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<real> P) {
+__global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepParams<real> Pin) {
     extern __shared__ __align__(128) unsigned char smem[];
+    SweepParams<real> P = Pin;
+    {   /* independent replicas of the same problem share J and h; everything else is per replica */
+        const int replica = P.replicaBase + (int)blockIdx.y;
+        P.seed += (unsigned long long)replica;
+        P.q += (size_t)replica * P.qReplicaStride;
+        const size_t ho = (size_t)replica * P.handoffReplicaStride / 8;
+        P.acceptFlags += ho; P.snapFlags += ho; P.snapBits += ho;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = P.N, m = P.m;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -513,20 +524,22 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(SweepParams<re
 
 /* ---------------- small element-wise kernels ---------------- */
 __global__ void randomizeSpinKernel(signed char *q, int ldq, int N, int m, unsigned long long seed,
-                                    unsigned long long count, unsigned domain, int yOff) {
+                                    unsigned long long count, unsigned domain, int yOff, int mPerReplica) {
     /* one Philox call per 128 spins (reference: DeviceKernels.cu:549-572 takes the LSB of a pool word per spin) */
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     int groups = (N + 127) >> 7;
     if (g >= groups * m) return;
     int y = g / groups, grp = g % groups;
-    Philox4 p = sqbPhilox(seed, count, domain, (uint32_t)grp, (uint32_t)(y + yOff));
+    /* rows are [replica][trotter]; replica r draws from seed + r, exactly like a separate solver seeded seed + r */
+    const int rp = mPerReplica > 0 ? y / mPerReplica : 0, yy = mPerReplica > 0 ? y % mPerReplica : y;
+    Philox4 p = sqbPhilox(seed + (unsigned long long)rp, count, domain, (uint32_t)grp, (uint32_t)(yy + yOff));
     signed char *row = q + (size_t)y * ldq;
     int x0 = grp << 7;
     for (int k = 0; k < 128 && x0 + k < N; ++k) row[x0 + k] = ((p.w[(k >> 5) & 3] >> (k & 31)) & 1u) ? 1 : -1;
 }
 
 __global__ void broadcastSpinRowKernel(signed char *q, int ldq, int N, int m, const signed char *src) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    int x = blockIdx.y * blockDim.x + threadIdx.x, y = blockIdx.x; /* rows on grid.x */
     if (x < N && y < m) q[(size_t)y * ldq + x] = src[x];
 }
 
@@ -541,9 +554,9 @@ __global__ void ringSpinDotKernel(const signed char *q, int ldq, int N, int m, l
 }
 
 void launchRandomizeSpin(const B200Device &dev, signed char *q, int ldq, int N, int m, unsigned long long seed,
-                         unsigned long long count, unsigned domain, int yOff) {
+                         unsigned long long count, unsigned domain, int yOff, int mPerReplica) {
     int groups = ((N + 127) >> 7) * m;
-    randomizeSpinKernel<<<(groups + 127) / 128, 128, 0, dev.stream()>>>(q, ldq, N, m, seed, count, domain, yOff);
+    randomizeSpinKernel<<<(groups + 127) / 128, 128, 0, dev.stream()>>>(q, ldq, N, m, seed, count, domain, yOff, mPerReplica);
     CUDA_CHECK(cudaGetLastError());
     ++dev.launchCount;
 }
@@ -588,6 +601,7 @@ template <class real> B200DenseGraphAnnealer<real>::B200DenseGraphAnnealer()
     : dev_(NULL), ldJ_(0), ldq_(0), c_(0), seed_(0), step_(0), randomizeCount_(0), launchCount_(0), nWindows_(0) {
     handoff_ = NULL; handoffIpc_ = false; peerBase_[0] = peerBase_[1] = NULL;
     ringRank_ = 0; ringWorld_ = 1; mRing_ = 0; yOff_ = 0; ringEpoch_ = 0;
+    nReplicas_ = 1; replicasPerLaunch_ = 1;
     m_ = -1;
     selectAlgorithm(sq::algoDefault);
 }
@@ -702,14 +716,23 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     setState(solRandSeedGiven);
     if (m_ == 1) selectDefaultSAAlgorithm(algo_, sq::algoSANaive);
 
+    sqb_throwErrorIf(nReplicas_ > 1 && ringWorld_ > 1, "replica batches and ring sharding cannot be combined.");
+    const int rows = m_ * nReplicas_;
     ldq_ = sq::roundUp(N_, 16);
-    dq_.alloc(dev_, (size_t)m_ * ldq_);
-    dE_.alloc(dev_, m_);
-    E_.resize(m_);
-    hq_.assign((size_t)m_ * ldq_, 0);
+    dq_.alloc(dev_, (size_t)rows * ldq_);
+    dE_.alloc(dev_, rows);
+    E_.resize(rows);
+    hq_.assign((size_t)rows * ldq_, 0);
 
     /* launch geometry of the sweep */
-    const int G = std::min(dev_->numSMs(), (int)m_);
+    /* CTAs per replica: the whole device for one replica; with a batch, as few as the 32-trotters-per-CTA limit allows so
+     * that many replicas run side by side in one cooperative launch */
+    int G = std::min(dev_->numSMs(), (int)m_);
+    if (nReplicas_ > 1) {
+        const int gMin = (m_ + 31) / 32;
+        G = std::max(gMin, std::min(G, dev_->numSMs() / std::min(nReplicas_, dev_->numSMs())));
+    }
+    replicasPerLaunch_ = std::max(1, std::min(nReplicas_, dev_->numSMs() / G));
     const int maxT = (m_ + G - 1) / G;
     const int nw64 = packedWords64(N_);
     int chunkElems = std::min((int)ldJ_, (int)(4096 / sizeof(real)));
@@ -745,7 +768,8 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
 
 template <class real> void B200DenseGraphAnnealer<real>::randomizeSpin() {
     throwErrorIfNotPrepared();
-    launchRandomizeSpin(*dev_, dq_.p, ldq_, N_, m_, seed_, randomizeCount_++, DOM_RANDOMIZE, ringWorld_ > 1 ? yOff_ : 0);
+    launchRandomizeSpin(*dev_, dq_.p, ldq_, N_, m_ * nReplicas_, seed_, randomizeCount_++, DOM_RANDOMIZE, ringWorld_ > 1 ? yOff_ : 0,
+                        nReplicas_ > 1 ? m_ : 0);
     setState(solQSet);
 }
 
@@ -755,8 +779,8 @@ template <class real> void B200DenseGraphAnnealer<real>::set_q(const sq::BitSet 
     DevBuf<signed char> tmp;
     tmp.alloc(dev_, N_);
     dev_->h2d(tmp.p, q.data, N_);
-    dim3 grid((N_ + 127) / 128, m_);
-    broadcastSpinRowKernel<<<grid, 128, 0, dev_->stream()>>>(dq_.p, ldq_, N_, m_, tmp.p);
+    dim3 grid(m_ * nReplicas_, (N_ + 127) / 128);
+    broadcastSpinRowKernel<<<grid, 128, 0, dev_->stream()>>>(dq_.p, ldq_, N_, m_ * nReplicas_, tmp.p);
     CUDA_CHECK(cudaGetLastError());
     ++dev_->launchCount;
     dev_->synchronize();
@@ -767,9 +791,14 @@ template <class real> void B200DenseGraphAnnealer<real>::set_qset(const sq::BitS
     sqb_throwErrorIf(q.size() == 0, "empty q set.");
     for (int i = 0; i < q.size(); ++i)
         sqb_throwErrorIf(q[i].size != N_, "Dimension of q, %d, should be equal to N, %d.", q[i].size, N_);
-    m_ = q.size();
-    prepare(); /* CUDADenseGraphAnnealer.cu:216-218: the number of trotters follows the set */
-    for (int y = 0; y < m_; ++y) memcpy(&hq_[(size_t)y * ldq_], q[y].data, N_);
+    if (nReplicas_ > 1) {
+        sqb_throwErrorIf(q.size() != m_ * nReplicas_, "replica batch: expected %d x %d spin rows.", nReplicas_, m_);
+        if (!isPrepared()) prepare();
+    } else {
+        m_ = q.size();
+        prepare(); /* CUDADenseGraphAnnealer.cu:216-218: the number of trotters follows the set */
+    }
+    for (int y = 0; y < m_ * nReplicas_; ++y) memcpy(&hq_[(size_t)y * ldq_], q[y].data, N_);
     dev_->h2d(dq_.p, hq_.data(), hq_.size());
     dev_->synchronize();
     setState(solQSet);
@@ -778,15 +807,18 @@ template <class real> void B200DenseGraphAnnealer<real>::set_qset(const sq::BitS
 template <class real> void B200DenseGraphAnnealer<real>::setSpinsRaw(const signed char *q, int m) {
     /* C-ABI fast path of set_qset: q is m x N, contiguous */
     throwErrorIfProblemNotSet();
-    if (m != m_ || !isPrepared()) { m_ = m; prepare(); }
-    dev_->h2d2D(dq_.p, ldq_, q, N_, N_, m_);
+    if (nReplicas_ > 1) {
+        sqb_throwErrorIf(m != m_ * nReplicas_, "replica batch: expected %d x %d spin rows, got %d.", nReplicas_, m_, m);
+        if (!isPrepared()) prepare();
+    } else if (m != m_ || !isPrepared()) { m_ = m; prepare(); }
+    dev_->h2d2D(dq_.p, ldq_, q, N_, N_, m_ * nReplicas_);
     dev_->synchronize();
     setState(solQSet);
 }
 
 template <class real> void B200DenseGraphAnnealer<real>::getSpinsRaw(signed char *q) const {
     throwErrorIfQNotSet();
-    dev_->d2h2D(q, N_, dq_.p, ldq_, N_, m_);
+    dev_->d2h2D(q, N_, dq_.p, ldq_, N_, m_ * nReplicas_);
     dev_->synchronize();
 }
 
@@ -795,7 +827,7 @@ template <class real> void B200DenseGraphAnnealer<real>::syncBits() {
     qlist_.clear();
     dev_->d2h(hq_.data(), dq_.p, hq_.size());
     dev_->synchronize();
-    for (int y = 0; y < m_; ++y) {
+    for (int y = 0; y < m_ * nReplicas_; ++y) {
         sq::BitSet q(N_), x(N_);
         for (int i = 0; i < N_; ++i) {
             char v = hq_[(size_t)y * ldq_ + i];
@@ -827,12 +859,12 @@ template <class real> void B200DenseGraphAnnealer<real>::calculate_E() {
     bool done = false;
     if constexpr (std::is_same<real, float>::value) {
         if (tcJ_.ready && tcEnabled()) {
-            tcBatchedEnergy(*dev_, dE_.p, tcJ_, dq_.p, ldq_, dq_.p, ldq_, dh_.p, NULL, m_, -sign, -sign * c_, tcWs_);
+            tcBatchedEnergy(*dev_, dE_.p, tcJ_, dq_.p, ldq_, dq_.p, ldq_, dh_.p, NULL, m_ * nReplicas_, -sign, -sign * c_, tcWs_);
             done = true;
         }
     }
-    if (!done) devBatchedEnergy<real>(*dev_, dE_.p, dJ_.p, ldJ_, N_, N_, dq_.p, ldq_, dq_.p, ldq_, dh_.p, NULL, m_, -sign, -sign * c_);
-    dev_->d2h(E_.data, dE_.p, sizeof(real) * m_);
+    if (!done) devBatchedEnergy<real>(*dev_, dE_.p, dJ_.p, ldJ_, N_, N_, dq_.p, ldq_, dq_.p, ldq_, dh_.p, NULL, m_ * nReplicas_, -sign, -sign * c_);
+    dev_->d2h(E_.data, dE_.p, sizeof(real) * m_ * nReplicas_);
     dev_->synchronize();
     setState(solEAvailable);
 }
@@ -846,6 +878,7 @@ template <class real> void B200DenseGraphAnnealer<real>::makeSolution() {
 
 template <class real> real B200DenseGraphAnnealer<real>::getSystemE(real G, real beta) const {
     This *self = const_cast<This *>(this);
+    sqb_throwErrorIf(nReplicas_ > 1, "getSystemE is defined per solver instance; not available on a replica batch.");
     self->calculate_E();
     real E = E_.sum() / m_;
     if (sq::isSQAAlgorithm(algo_)) {
@@ -896,11 +929,17 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
     P.roundBase = (launchCount_ + 1ull) * (unsigned long long)(N_ + SW_FLAG_RING);
     P.snapBase = (launchCount_ + 1ull) * (unsigned long long)(nWindows_ + 2);
     P.stats = dStats_.p;
+    P.qReplicaStride = (size_t)m_ * ldq_;
+    P.handoffReplicaStride = hl.total;
     void *args[] = {&P};
     const void *fn = sweepKernelFor<real>(sqa, K_);
     dev_->makeCurrent();
-    CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid_), dim3(SW_THREADS), args, smemBytes_, dev_->stream()));
-    ++dev_->launchCount;
+    for (int base = 0; base < nReplicas_; base += replicasPerLaunch_) {
+        P.replicaBase = base;
+        const int nr = std::min(replicasPerLaunch_, nReplicas_ - base);
+        CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid_, nr), dim3(SW_THREADS), args, smemBytes_, dev_->stream()));
+        ++dev_->launchCount;
+    }
     ++launchCount_;
     ++step_;
     if (ringWorld_ > 1) ringPushHalos(); /* per-sweep boundary exchange over NVLink */
@@ -919,11 +958,11 @@ template <class real> void B200DenseGraphAnnealer<real>::allocHandoff() {
     handoffIpc_ = ringWorld_ > 1;
     if (handoffIpc_) { /* plain cudaMalloc: exportable with cudaIpcGetMemHandle (pool memory is not) */
         dev_->makeCurrent();
-        CUDA_CHECK(cudaMalloc(&handoff_, hl.total));
-        CUDA_CHECK(cudaMemsetAsync(handoff_, 0, hl.total, dev_->stream()));
+        CUDA_CHECK(cudaMalloc(&handoff_, hl.total * nReplicas_));
+        CUDA_CHECK(cudaMemsetAsync(handoff_, 0, hl.total * nReplicas_, dev_->stream()));
         dev_->synchronize();
     } else
-        handoff_ = dev_->alloc(hl.total);
+        handoff_ = dev_->alloc(hl.total * nReplicas_);
     for (int side = 0; side < 2; ++side) closePeer(side);
     ringEpoch_ = 0;
 }
@@ -935,6 +974,12 @@ template <class real> void B200DenseGraphAnnealer<real>::closePeer(int side) {
         peerBase_[side] = NULL;
     }
 }
+template <class real> void B200DenseGraphAnnealer<real>::setNumReplicas(int n) {
+    sqb_throwErrorIf(n < 1, "number of replicas must be positive.");
+    if (n != nReplicas_) clearState(solPrepared);
+    nReplicas_ = n;
+}
+
 template <class real> void B200DenseGraphAnnealer<real>::ringConfigure(int rank, int world, int mGlobal) {
     sqb_throwErrorIf(world < 1 || rank < 0 || rank >= world, "ring sharding: invalid rank %d / world %d.", rank, world);
     sqb_throwErrorIf(mGlobal % world != 0 || mGlobal / world < 2, "ring sharding: n_trotters (%d) must be a multiple of the number "

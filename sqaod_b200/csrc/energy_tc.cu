@@ -70,7 +70,7 @@ tcSpinGemmKernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     uint32_t *tmemBaseSlot = reinterpret_cast<uint32_t *>(tmemFullBar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
+    const int n0 = blockIdx.y * TC_BN, m0 = blockIdx.x * TC_BM; /* batch tiles on grid.x (may exceed 65535 / 128 rows) */
     const int numKB = 3 * kBlocksPerSplit;
 
     if (threadIdx.x == 0) {
@@ -173,7 +173,7 @@ tcSpinGemmKernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 
 /* ---- operand preparation ---- */
 __global__ void tcSplitKernel(__nv_bfloat16 *out, int rowsPad, int Kp, const float *A, int ldA, int rows, int K) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x, r = blockIdx.x; /* rows on grid.x: no 65535 limit */
     if (k >= K || r >= rows) return;
     const float a = A[(size_t)r * ldA + k];
     const __nv_bfloat16 hi = __float2bfloat16_rn(a);
@@ -187,7 +187,7 @@ __global__ void tcSplitKernel(__nv_bfloat16 *out, int rowsPad, int Kp, const flo
     out[2 * plane + at] = lo;
 }
 __global__ void tcWidenSpinsKernel(__nv_bfloat16 *out, int Kp, const signed char *Q, int ldq, int m, int K) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x, r = blockIdx.x;
     if (k >= Kp || r >= m) return;
     out[(size_t)r * Kp + k] = __float2bfloat16_rn(k < K ? (float)Q[(size_t)r * ldq + k] : 0.f);
 }
@@ -231,7 +231,7 @@ void tcPrepareOperand(const B200Device &dev, TcOperand &op, const float *d_A, in
     op.rowsPad = sq::roundUp(rows, TC_BN);
     op.Kp = sq::roundUp(K, TC_BK);
     op.data.alloc(&dev, (size_t)3 * op.rowsPad * op.Kp); /* zero filled: padding rows / columns contribute nothing */
-    dim3 grid((K + 127) / 128, rows);
+    dim3 grid(rows, (K + 127) / 128);
     tcSplitKernel<<<grid, 128, 0, dev.stream()>>>((__nv_bfloat16 *)op.data.p, op.rowsPad, op.Kp, d_A, ldA, rows, K);
     CUDA_CHECK(cudaGetLastError());
     ++dev.launchCount;
@@ -245,7 +245,7 @@ void tcSpinGemm(const B200Device &dev, float *d_C, int ldc, const TcOperand &B, 
     const size_t need = (size_t)mPad * B.Kp;
     if (ws.qbf.n < need || ws.qbf.dev != &dev) ws.qbf.alloc(&dev, need);
     ws.dev = &dev;
-    dim3 wgrid((B.Kp + 127) / 128, m);
+    dim3 wgrid(m, (B.Kp + 127) / 128);
     tcWidenSpinsKernel<<<wgrid, 128, 0, dev.stream()>>>((__nv_bfloat16 *)ws.qbf.p, B.Kp, d_Q, ldq, m, B.K);
     CUtensorMap mapQ;
     makeMap(&mapQ, ws.qbf.p, mPad, B.Kp, TC_BM);
@@ -254,7 +254,7 @@ void tcSpinGemm(const B200Device &dev, float *d_C, int ldc, const TcOperand &B, 
         CUDA_CHECK(cudaFuncSetAttribute(tcSpinGemmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
         attrSet = true;
     }
-    dim3 grid((B.rows + TC_BN - 1) / TC_BN, (m + TC_BM - 1) / TC_BM);
+    dim3 grid((m + TC_BM - 1) / TC_BM, (B.rows + TC_BN - 1) / TC_BN);
     tcSpinGemmKernel<<<grid, TC_THREADS, TC_SMEM_BYTES, dev.stream()>>>(mapQ, *(const CUtensorMap *)B.map, d_C, ldc, m, B.rows, B.rowsPad,
                                                                         B.Kp / TC_BK);
     CUDA_CHECK(cudaGetLastError());

@@ -121,20 +121,25 @@ def anneal_replicas(W, n_replicas, schedule, beta, dtype=np.float32, n_trotters=
     prefs = {'algorithm': algorithm}
     if n_trotters is not None:
         prefs['n_trotters'] = n_trotters
-    ann = solvers.dense_graph_annealer(W, opt, dtype, **prefs)   # J is uploaded once per rank and reused by its replicas
-    best = np.full(max(end - begin, 0), np.inf if minimize else -np.inf)
+    n_local = end - begin
+    best = np.full(max(n_local, 0), np.inf if minimize else -np.inf)
     best_q, best_id = None, -1
-    for k, r in enumerate(range(begin, end)):
-        ann.seed(replica_seed(base_seed, rank, r))
+    if n_local > 0:
+        # one solver per rank: J uploaded once, the rank's replicas annealed side by side (seed base + r for replica r)
+        ann = solvers.dense_graph_annealer(W, opt, dtype, **prefs)
+        ann.set_replicas(n_local)
+        ann.seed(replica_seed(base_seed, rank, begin))
         ann.prepare()
         ann.randomize_spin()
         for G in schedule:
             ann.anneal_one_step(G, beta)
-        E = ann.get_E()
-        i = int(np.argmin(E) if minimize else np.argmax(E))
-        best[k] = E[i]
-        if best_id < 0 or (E[i] < best[best_id - begin] if minimize else E[i] > best[best_id - begin]):
-            best_id, best_q = r, ann.get_spins()[i].copy()
+        m = ann.get_preferences()['n_trotters']
+        E = ann.get_E().reshape(n_local, m)
+        idx = np.argmin(E, axis=1) if minimize else np.argmax(E, axis=1)
+        best = E[np.arange(n_local), idx].astype(np.float64)
+        k = int(np.argmin(best) if minimize else np.argmax(best))
+        best_id = begin + k
+        best_q = ann.get_spins().reshape(n_local, m, -1)[k, idx[k]].copy()
     local_best = (best.min() if minimize else best.max()) if len(best) else (np.inf if minimize else -np.inf)
     return best_energy_over_ranks(local_best, minimize, group), best, best_id, best_q
 

@@ -113,9 +113,15 @@ class DenseGraphAnnealer(_SolverBase):
         return n.value
 
     def _m(self):
-        m = C.c_int(0)
+        """rows of the spin / energy buffers: n_trotters (x n_replicas for a replica batch)"""
+        m = C.c_int(0); r = C.c_int(1)
         _lib.check(L.sqb_dg_annealer_get_num_trotters(self._cobj, C.byref(m), self._dt))
-        return m.value
+        _lib.check(L.sqb_dg_annealer_get_num_replicas(self._cobj, C.byref(r), self._dt))
+        return m.value * r.value
+
+    def set_replicas(self, n_replicas):
+        """anneal n_replicas independent replicas (seed, seed+1, ...) side by side; call before prepare()."""
+        _lib.check(L.sqb_dg_annealer_set_num_replicas(self._cobj, int(n_replicas), self._dt))
 
     def get_hamiltonian(self):
         N = self.get_problem_size()

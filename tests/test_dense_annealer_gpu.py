@@ -161,3 +161,27 @@ def test_set_q_get_q_roundtrip(sq):
     assert ann.get_preferences()['n_trotters'] == m + 3
     assert np.array_equal(np.stack(ann.get_q()), qs)
     assert np.array_equal(np.stack(ann.get_x()), (qs + 1) // 2)
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('N,m,R,algo', [(64, 8, 5, 'coloring'), (200, 70, 40, 'coloring'), (96, 1, 7, 'sa_naive'), (128, 33, 200, 'coloring')])
+def test_replica_batch_equals_separate_solvers(sq, N, m, R, algo, dtype):
+    """R replicas annealed side by side in one launch == R separate solvers seeded seed + r (spin for spin)."""
+    W = quantized_symmetric_W(N, 31 + N, dtype)
+    seed = 100
+    batch = sq.dense_graph_annealer(W, sq.minimize, dtype, n_trotters=m, algorithm=algo)
+    batch.set_replicas(R)
+    batch.seed(seed); batch.prepare(); batch.randomize_spin()
+    Gs = [2.0, 1.0, 0.4]
+    for G in Gs:
+        batch.anneal_one_step(G, 1. / 0.3)
+    qb = batch.get_spins().reshape(R, m, N)
+    Eb = batch.get_E().reshape(R, m)
+    for r in sorted(set([0, 1, R // 2, R - 1])):
+        one = sq.dense_graph_annealer(W, sq.minimize, dtype, n_trotters=m, algorithm=algo)
+        one.seed(seed + r); one.prepare(); one.randomize_spin()
+        for G in Gs:
+            one.anneal_one_step(G, 1. / 0.3)
+        assert np.array_equal(one.get_spins(), qb[r]), 'replica %d differs' % r
+        assert np.allclose(one.get_E(), Eb[r], rtol=tol(dtype), atol=tol(dtype) * 10)
+    assert len(batch.get_q()) == R * m

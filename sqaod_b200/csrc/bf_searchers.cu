@@ -70,9 +70,12 @@ __host__ __device__ __forceinline__ double fromOrderedKey(unsigned long long k) 
                 if (at < P.outCap) P.outX[at] = xBase | (s_ ^ (s_ >> 1));                     \
             }                                                                                 \
         } else                                                                                \
-            Emin = fmin(Emin, E_);                                                            \
+            Emin = (E_ < Emin) ? E_ : Emin; /* energies are finite: no NaN handling needed */   \
     }
 #define BF_FLIP(D) { A += D; D = -D; }
+/* bits 0..2 of the Gray code are 0 at every multiple of 16, so inside a 16-block their flips alternate 0->1, 1->0 */
+#define BF_SET(D) { A += D; }
+#define BF_CLR(D) { A -= D; }
 
 template <bool COLLECT> __global__ void __launch_bounds__(512, 2) bfKernel(BFParams P) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -139,21 +142,21 @@ template <bool COLLECT> __global__ void __launch_bounds__(512, 2) bfKernel(BFPar
                 const int nBlocks = 1 << (L - 4);
                 for (int q = 0; q < nBlocks; ++q) {
                     const int s0 = q << 4;
-                    BF_VISIT(s0 + 0)  BF_FLIP(d[0])
-                    BF_VISIT(s0 + 1)  BF_FLIP(d[1])
-                    BF_VISIT(s0 + 2)  BF_FLIP(d[0])
-                    BF_VISIT(s0 + 3)  BF_FLIP(d[2])
-                    BF_VISIT(s0 + 4)  BF_FLIP(d[0])
-                    BF_VISIT(s0 + 5)  BF_FLIP(d[1])
-                    BF_VISIT(s0 + 6)  BF_FLIP(d[0])
+                    BF_VISIT(s0 + 0)  BF_SET(d[0])
+                    BF_VISIT(s0 + 1)  BF_SET(d[1])
+                    BF_VISIT(s0 + 2)  BF_CLR(d[0])
+                    BF_VISIT(s0 + 3)  BF_SET(d[2])
+                    BF_VISIT(s0 + 4)  BF_SET(d[0])
+                    BF_VISIT(s0 + 5)  BF_CLR(d[1])
+                    BF_VISIT(s0 + 6)  BF_CLR(d[0])
                     BF_VISIT(s0 + 7)  BF_FLIP(d[3])
-                    BF_VISIT(s0 + 8)  BF_FLIP(d[0])
-                    BF_VISIT(s0 + 9)  BF_FLIP(d[1])
-                    BF_VISIT(s0 + 10) BF_FLIP(d[0])
-                    BF_VISIT(s0 + 11) BF_FLIP(d[2])
-                    BF_VISIT(s0 + 12) BF_FLIP(d[0])
-                    BF_VISIT(s0 + 13) BF_FLIP(d[1])
-                    BF_VISIT(s0 + 14) BF_FLIP(d[0])
+                    BF_VISIT(s0 + 8)  BF_SET(d[0])
+                    BF_VISIT(s0 + 9)  BF_SET(d[1])
+                    BF_VISIT(s0 + 10) BF_CLR(d[0])
+                    BF_VISIT(s0 + 11) BF_CLR(d[2])
+                    BF_VISIT(s0 + 12) BF_SET(d[0])
+                    BF_VISIT(s0 + 13) BF_CLR(d[1])
+                    BF_VISIT(s0 + 14) BF_CLR(d[0])
                     BF_VISIT(s0 + 15)
                     if (q + 1 < nBlocks) {
                         switch (__ffs(q + 1) + 3) { /* bit flipped by the step 16q+15 -> 16(q+1) */

@@ -236,7 +236,7 @@ def main():
                        'l2': 'J is %d MiB > 126 MB L2 and rows are drawn at random, no flush needed' % (N * N * 4 >> 20),
                        'acceptance_rate': accepted / float(attempts_per_step * args.steps),
                        'flag_waits': stats1['flag_waits'] - stats0['flag_waits'],
-                       'barrier_ms_per_step': {k: (stats1['barrier_cycles_' + k] - stats0['barrier_cycles_' + k]) / 148.0 / 1.965e6 / args.steps
+                       'busy_ms_per_step_per_cta': {k: (stats1['barrier_cycles_' + k] - stats0['barrier_cycles_' + k]) / 148.0 / 1.965e6 / args.steps
                                                for k in ('dot', 'chain')}},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'attempts/s', 'h2d_bytes_per_step': m * N, 'd2h_bytes_per_step': m * N + m * 4,

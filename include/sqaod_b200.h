@@ -81,7 +81,8 @@ int sqb_dg_annealer_anneal_one_step(sqb_handle ann, double G, double beta, int d
  * building solution lists (device int8 matrix <-> host m x N buffer) */
 int sqb_dg_annealer_get_stats(sqb_handle ann, unsigned long long *accepted, unsigned long long *waits, int dtype);
 int sqb_dg_annealer_get_spins(sqb_handle ann, signed char *q, int dtype);
-/* SM cycles lane 0 of dot warp 0 / of the chain warp spent at the end-of-window barrier, summed over CTAs (profiling aid) */
+/* SM cycles dot warp 0 / the chain warp spent working inside the look-ahead windows, summed over CTAs (profiling aid:
+ * whichever is larger paces the sweep) */
 int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, unsigned long long *chain, int dtype);
 
 /* replica batch (no reference counterpart): R independent replicas of the problem, replica r seeded

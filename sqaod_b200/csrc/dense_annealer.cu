@@ -33,6 +33,8 @@
 #include <type_traits>
 #include <time.h>
 #include <algorithm>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace sqb {
 
@@ -45,6 +47,7 @@ template <class real> struct SweepParams {
     int ldJ, ldq, N, m;
     unsigned long long seed, step;
     real twoDivM, coef, beta;
+    real scaleA, scaleNb; /* accept iff q (scaleA (h + 2 sum) - scaleNb (ql + qr)) < -ln u : scaleA = beta 2/m (SA: 2/kT), scaleNb = beta coef */
     int chunkElems, chunksPerRow, stages, nw64, K;
     /* hand-off arrays have m + 2 slots: local trotter l -> slot l; slot m / m + 1 = the trotter left of local 0 / right of
      * local m-1 when it lives on another GPU (ring sharding); the owning GPU mirrors its publications into them */
@@ -61,12 +64,12 @@ template <class real> struct SweepParams {
     unsigned long long stepEpoch;
     unsigned long long *peerFlags[2], *peerSnapFlags[2], *peerSnapBits[2]; /* the peers' arrays (NVLink P2P), or NULL */
     unsigned long long roundBase, snapBase;
-    unsigned long long *stats;       /* [0] accepted flips, [1] remote wait polls, [2]/[3] barrier-wait cycles of dot warp 0 / chain warp */
+    unsigned long long *stats;       /* [0] accepted flips, [1] remote wait polls, [2]/[3] busy cycles of dot warp 0 / the chain warp, summed over CTAs */
 };
 
 /* shared-memory carve-up, identical on host and device */
 template <class real> struct SweepSmem {
-    size_t ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, us, hs, xn, conf, total;
+    size_t ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, total;
     __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K) {
         size_t o = 0;
         ring = o; o += (size_t)SW_DOT_WARPS * stages * chunkElems * sizeof(real);
@@ -78,6 +81,7 @@ template <class real> struct SweepSmem {
         o = (o + 15) & ~(size_t)15;
         cross = o; o += (size_t)2 * T * K * (2 * K) * sizeof(real);
         xs = o; o += (size_t)3 * T * K * 4;
+        xb = o; o += (size_t)3 * T * K * 4;
         o = (o + 15) & ~(size_t)15;
         us = o; o += (size_t)3 * T * K * sizeof(real);
         hs = o; o += (size_t)3 * T * K * sizeof(real);
@@ -87,6 +91,21 @@ template <class real> struct SweepSmem {
     }
 };
 
+/* -ln(u) for the accept test exp(-dE beta) > u  <=>  dE beta < -ln(u).  u == 1 (possible after rounding to fp32) never
+ * accepts, like `1 > u` in the reference; u == 0 accepts whenever exp() would not underflow to zero. */
+template <class real> __device__ __forceinline__ real negLogUniform(const Philox4 &p);
+template <> __device__ __forceinline__ float negLogUniform<float>(const Philox4 &p) {
+    const float u = philoxUniform<float>(p);
+    if (u >= 1.f) return -INFINITY;
+    if (u <= 0.f) return 103.f;
+    return -logf(u);
+}
+template <> __device__ __forceinline__ double negLogUniform<double>(const Philox4 &p) {
+    const double u = philoxUniform<double>(p);
+    if (u >= 1.) return -INFINITY;
+    if (u <= 0.) return 745.;
+    return -log(u);
+}
 template <class real> __device__ __forceinline__ real expReal(real v);
 template <> __device__ __forceinline__ float expReal<float>(float v) { return expf(v); }
 template <> __device__ __forceinline__ double expReal<double>(double v) { return exp(v); }
@@ -116,16 +135,16 @@ __device__ __forceinline__ int sweepPhase(int y, int m) { /* 0: even, 1: trotter
 }
 
 template <class real, bool SQA, int K>
-__global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepParams<real> Pin) {
+__global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepParams<real> P) {
     extern __shared__ __align__(128) unsigned char smem[];
-    SweepParams<real> P = Pin;
-    {   /* independent replicas of the same problem share J and h; everything else is per replica */
-        const int replica = P.replicaBase + (int)blockIdx.y;
-        P.seed += (unsigned long long)replica;
-        P.q += (size_t)replica * P.qReplicaStride;
-        const size_t ho = (size_t)replica * P.handoffReplicaStride / 8;
-        P.acceptFlags += ho; P.snapFlags += ho; P.snapBits += ho;
-    }
+    /* independent replicas of the same problem share J and h; seed, spins and hand-off block are per replica */
+    const int replica = P.replicaBase + (int)blockIdx.y;
+    const unsigned long long seedR = P.seed + (unsigned long long)replica;
+    signed char *const qBase = P.q + (size_t)replica * P.qReplicaStride;
+    const size_t handoffOff = (size_t)replica * P.handoffReplicaStride / 8;
+    unsigned long long *const aFlags = P.acceptFlags + handoffOff;
+    unsigned long long *const sFlags = P.snapFlags + handoffOff;
+    unsigned long long *const sBits = P.snapBits + handoffOff;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = P.N, m = P.m;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -146,6 +165,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     real *dots = reinterpret_cast<real *>(smem + L.dots);    /* [2][maxT][K] */
     real *cross = reinterpret_cast<real *>(smem + L.cross);  /* [2][maxT][K][2K] */
     int *xs = reinterpret_cast<int *>(smem + L.xs);          /* [3][maxT][K] */
+    int *xb = reinterpret_cast<int *>(smem + L.xb);          /* [3][maxT][K]: (32-bit word index << 5) | bit of spin x in a packed row */
     real *us = reinterpret_cast<real *>(smem + L.us);
     real *hs = reinterpret_cast<real *>(smem + L.hs);
     int *xn = reinterpret_cast<int *>(smem + L.xn);          /* [2 sides][3][K] */
@@ -176,17 +196,22 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         const int Kw = roundsIn(w), slot = w % 3;
         for (int idx = t0; idx < Kw * T; idx += nthr) {
             int t = idx % T, rl = idx / T;
-            Philox4 p = sqbPhilox(P.seed, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)gOf(y0 + t));
+            Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)gOf(y0 + t));
             int x = (int)(p.w[0] % (uint32_t)N);
             int o = (slot * maxT + t) * K + rl;
             xs[o] = x;
-            us[o] = philoxUniform<real>(p);
+            {
+                int w64, bit;
+                spinBitPos(x, w64, bit);
+                xb[o] = ((2 * w64 + (bit >> 5)) << 5) | (bit & 31);
+            }
+            us[o] = negLogUniform<real>(p); /* accept iff dE*beta < -ln(u): no exp on the chain's critical path */
             hs[o] = P.h[x];
         }
         if (remote) {
             for (int idx = t0; idx < 2 * Kw; idx += nthr) {
                 int side = idx / Kw, rl = idx % Kw;
-                Philox4 p = sqbPhilox(P.seed, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)(side ? yRight : yLeft));
+                Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)(side ? yRight : yLeft));
                 xn[(side * 3 + slot) * K + rl] = (int)(p.w[0] % (uint32_t)N);
             }
         }
@@ -214,10 +239,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         for (int idx = tid; idx < rows * n4; idx += SW_THREADS) {
             int r = idx / n4, j = (idx % n4) << 2;
             const signed char *rowp;
-            if (r < T) rowp = P.q + (size_t)(y0 + r) * P.ldq;
+            if (r < T) rowp = qBase + (size_t)(y0 + r) * P.ldq;
             else {
                 const int sl = (r == T) ? slotL : slotR;
-                rowp = (sl < m) ? P.q + (size_t)sl * P.ldq : P.haloQ[sl - m];
+                rowp = (sl < m) ? qBase + (size_t)sl * P.ldq : P.haloQ[sl - m];
             }
             const signed char *src = rowp + j;
             unsigned nib = 0;
@@ -255,7 +280,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             skipEmptyWindows(iw, iid);
             if (iw >= nW) { issueDone = true; return; }
             int t = iid % T, rl = iid / T;
-            Philox4 p = sqbPhilox(P.seed, P.step, DOM_DENSE_SWEEP, (uint32_t)(iw * K + rl), (uint32_t)gOf(y0 + t));
+            Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(iw * K + rl), (uint32_t)gOf(y0 + t));
             ix = (int)(p.w[0] % (uint32_t)N);
         }
         const int elems = min(CH, P.ldJ - ic * CH);
@@ -307,7 +332,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 if (++cStage == S) { cStage = 0; cParity ^= 1u; }
             }
             real s = warpSum((a0 + a1) + (a2 + a3));
-            if (lane == 0) dots[(buf * maxT + t) * K + rl] = s;
+            if (lane == 0) dots[(buf * maxT + t) * K + rl] = P.scaleA * (hs[((w % 3) * maxT + t) * K + rl] + real(2) * s);
             if (lane < 2 * K) cross[((buf * maxT + t) * K + rl) * (2 * K) + lane] = crossv;
         }
     };
@@ -331,12 +356,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     const unsigned long long *leftRow = lLocal ? qcur + (size_t)(yl - y0) * NW : nbsnap;
     const unsigned long long *rightRow = rLocal ? qcur + (size_t)(yr - y0) * NW : nbsnap + NW;
     const bool publishes = remote && active && (lane == 0 || lane == T - 1);
-    unsigned long long *myFlags = P.acceptFlags + (size_t)(active ? y : 0) * SW_FLAG_RING;
+    uint32_t *my32 = reinterpret_cast<uint32_t *>(myRow);
+    const uint32_t *left32 = reinterpret_cast<const uint32_t *>(leftRow), *right32 = reinterpret_cast<const uint32_t *>(rightRow);
+    const bool remoteMask = remote && (!lLocal || !rLocal);
+    unsigned long long *myFlags = aFlags + (size_t)(active ? y : 0) * SW_FLAG_RING;
     /* the first / last trotter of a sharded ring also publishes into the neighbouring GPU's arrays */
     unsigned long long *mirror0 = (ringSharded && active && y == 0 && P.peerFlags[0]) ? P.peerFlags[0] + (size_t)(m + 1) * SW_FLAG_RING : NULL;
     unsigned long long *mirror1 = (ringSharded && active && y == m - 1 && P.peerFlags[1]) ? P.peerFlags[1] + (size_t)m * SW_FLAG_RING : NULL;
     unsigned long long nAccepted = 0, nWaits = 0;
-    long long barrierWait = 0; /* cycles this warp's lane 0 spent at the end-of-window barrier */
 
     /* spin of a trotter owned by another CTA: published snapshot, corrected by the accept bits of the neighbour's
      * attempts that hit the same spin index since the snapshot */
@@ -353,7 +380,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 mask &= mask - 1;
                 long long rr = (long long)w * K + (j - K); /* j < K: previous window */
                 const unsigned long long want = P.roundBase + (unsigned long long)rr + 1ull;
-                const unsigned long long *f = P.acceptFlags + (size_t)(side ? slotR : slotL) * SW_FLAG_RING + (rr % SW_FLAG_RING);
+                const unsigned long long *f = aFlags + (size_t)(side ? slotR : slotL) * SW_FLAG_RING + (rr % SW_FLAG_RING);
                 /* the flag word carries its own payload (tag, accept bit): relaxed accesses are enough */
                 unsigned long long got = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f);
                 while ((got >> 1) != want) { ++nWaits; __nanosleep(20); got = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f); }
@@ -363,60 +390,73 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         return v;
     };
 
+    /* what chain window wn needs from the neighbouring CTAs: their snapshot S_{wn-1} and the masks of the neighbour attempts
+     * (previous + current window) that hit the spin index of my attempt rl */
+    auto chainHousekeeping = [&](int wn) __attribute__((always_inline)) {
+        if (!remote) return;
+        const int Kn = roundsIn(wn), slotN = wn % 3;
+        if (wn >= 2) {
+            for (int side = 0; side < 2; ++side) {
+                const int sl = side ? slotR : slotL;
+                if (lane == 0) {
+                    const unsigned long long want = P.snapBase + (unsigned long long)(wn - 1);
+                    if (ringSharded) { while (ldAcquireSys(sFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
+                    else { while (ldAcquire(sFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
+                }
+                __syncwarp();
+                const unsigned long long *src = sBits + ((size_t)sl * SW_SNAP_SLOTS + ((wn - 1) % SW_SNAP_SLOTS)) * NW;
+                for (int i = lane; i < NW; i += 32) nbsnap[(size_t)side * NW + i] = __ldcg(src + i);
+            }
+        }
+        for (int side = 0; side < 2; ++side) {
+            int nbx = -1;
+            if (lane < K) { if (wn > 0) nbx = xn[(side * 3 + (wn - 1) % 3) * K + lane]; }
+            else if (lane < 2 * K && lane - K < Kn) nbx = xn[(side * 3 + slotN) * K + (lane - K)];
+            const int tEdge = side ? T - 1 : 0;
+            for (int rl = 0; rl < Kn; ++rl) {
+                int xe = xs[(slotN * maxT + tEdge) * K + rl];
+                uint32_t hit = __ballot_sync(0xffffffffu, nbx == xe);
+                if (lane == 0) conf[side * K + rl] = hit;
+            }
+        }
+        __syncwarp();
+    };
+    if (chainWarp) chainHousekeeping(0);
+
+    long long cycLoop = 0, cycHk = 0, cycPrep = 0;
+    long long busy = 0; /* cycles lane 0 of this warp spent working inside the windows (dot warp 0 and the chain warp report it) */
     for (int w = 0; w < nW; ++w) {
+        /* BAR.SYNC blocks lazily (at the next use of barrier-protected state): touch shared memory before reading the clock so
+         * that the time spent waiting at the previous barrier is not booked as work */
+        { unsigned int dummy; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(dummy) : "r"(smemAddr(conf)) : "memory"); }
+        const long long tBusy0 = clock64();
         if (warp < SW_DOT_WARPS) {
             if (w + 1 < nW) dotWindow(w + 1);
+            busy += clock64() - tBusy0;
         } else {
-            /* ---- chain warp ---- */
+            /* ---- chain warp: replay window w, then prepare what window w+1 needs while the dot warps are still busy ---- */
             const int Kw = roundsIn(w), buf = w & 1, slot = w % 3;
-            if (remote) {
-                if (w >= 2) { /* neighbours' snapshot S_{w-1} (state before window w-1) */
-                    for (int side = 0; side < 2; ++side) {
-                        const int sl = side ? slotR : slotL;
-                        if (lane == 0) {
-                            const unsigned long long want = P.snapBase + (unsigned long long)(w - 1);
-                            if (ringSharded) { while (ldAcquireSys(P.snapFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
-                            else { while (ldAcquire(P.snapFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
-                        }
-                        __syncwarp();
-                        const unsigned long long *src = P.snapBits + ((size_t)sl * SW_SNAP_SLOTS + ((w - 1) % SW_SNAP_SLOTS)) * NW;
-                        for (int i = lane; i < NW; i += 32) nbsnap[(size_t)side * NW + i] = __ldcg(src + i);
-                    }
-                }
-                /* which neighbour attempts (previous + current window) hit the spin index of my attempt rl */
-                for (int side = 0; side < 2; ++side) {
-                    int nbx = -1;
-                    if (lane < K) { if (w > 0) nbx = xn[(side * 3 + (w - 1) % 3) * K + lane]; }
-                    else if (lane < 2 * K && lane - K < Kw) nbx = xn[(side * 3 + slot) * K + (lane - K)];
-                    const int tEdge = side ? T - 1 : 0;
-                    for (int rl = 0; rl < Kw; ++rl) {
-                        int xe = xs[(slot * maxT + tEdge) * K + rl];
-                        uint32_t hit = __ballot_sync(0xffffffffu, nbx == xe);
-                        if (lane == 0) conf[side * K + rl] = hit;
-                    }
-                }
-            }
-            __syncwarp();
-            /* (x, u, h) two windows ahead; reuses the ring slot of window w-1, so only after the masks above */
-            prepWindow(w + 2, lane, 32);
-            __syncwarp();
+            const real *dotRow = dots + (buf * maxT + (lane < T ? lane : 0)) * K;
+            const int tabBase = (slot * maxT + (lane < T ? lane : 0)) * K;
+            const real corrScale = real(-4) * P.scaleA; /* a flip of spin x' accepted since the snapshot changes sum by -2 q_old J[x][x'] */
+            const unsigned long long flagBase = (P.roundBase + (unsigned long long)w * K + 1ull) << 1;
+            const int flagSlot = (w * K) % SW_FLAG_RING;
+            /* table values of the lane's next attempt are fetched one round ahead (they do not depend on the state) */
+            int xbN = xb[tabBase];
+            real lnuN = us[tabBase], vN = dotRow[0];
             for (int rl = 0; rl < Kw; ++rl) {
 #pragma unroll 1
                 for (int ph = 0; ph < 3; ++ph) {
                     if (ph == 1 && !(mRing & 1)) continue;
                     if (active && myPhase == ph) {
-                        const int o = (slot * maxT + lane) * K + rl;
-                        const int x = xs[o];
-                        int w64, bit;
-                        spinBitPos(x, w64, bit);
-                        unsigned long long *word = myRow + w64;
-                        /* independent shared-memory reads first: own word, both neighbours' words, dot, h, u */
-                        const unsigned long long wv = *word, lv = leftRow[w64], rv = rightRow[w64];
-                        real sum = dots[(buf * maxT + lane) * K + rl];
-                        const real hx = hs[o], ux = us[o];
-                        const uint32_t cmL = lLocal ? 0u : conf[rl], cmR = rLocal ? 0u : conf[K + rl];
-                        const bool up = ((wv >> bit) & 1ull) != 0;
-                        const real qyx = up ? real(1) : real(-1);
+                        const int w32 = xbN >> 5, bit = xbN & 31;
+                        const real lnu = lnuN;
+                        real v = vN; /* scaleA (h + 2 sum) against the snapshot */
+                        /* state-dependent shared-memory reads: own word and both neighbours' words */
+                        const uint32_t wv = my32[w32], lv = left32[w32], rv = right32[w32];
+                        const uint32_t cm = remoteMask ? ((lLocal ? 0u : conf[rl]) | (rLocal ? 0u : conf[K + rl])) : 0u;
+                        if (rl + 1 < Kw) { xbN = xb[tabBase + rl + 1]; lnuN = us[tabBase + rl + 1]; vN = dotRow[rl + 1]; }
+                        const uint32_t up = (wv >> bit) & 1u;
                         /* repair the snapshot dot product with every flip accepted since the snapshot */
                         uint32_t ev = accP | ((accC & ((1u << rl) - 1u)) << K);
                         if (ev) {
@@ -425,48 +465,50 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                             do {
                                 int j = __ffs(ev) - 1;
                                 ev &= ev - 1;
-                                real qold = ((sg >> j) & 1u) ? real(1) : real(-1);
-                                sum += real(-2) * qold * cr[j];
+                                v += (((sg >> j) & 1u) ? corrScale : -corrScale) * cr[j];
                             } while (ev);
                         }
-                        real dE;
                         if (SQA) {
-                            int ql = ((lv >> bit) & 1ull) ? 1 : -1, qr = ((rv >> bit) & 1ull) ? 1 : -1;
-                            if (cmL | cmR) { /* rare: a neighbour owned by another CTA attempted this very spin */
-                                if (cmL) ql = remoteSpin(0, x, w, rl);
-                                if (cmR) qr = remoteSpin(1, x, w, rl);
+                            int nb = (int)((lv >> bit) & 1u) + (int)((rv >> bit) & 1u); /* number of up neighbours */
+                            if (cm) { /* rare: a neighbour owned by another CTA attempted this very spin */
+                                const int x = xs[tabBase + rl];
+                                int ql = ((lv >> bit) & 1u) ? 1 : -1, qr = ((rv >> bit) & 1u) ? 1 : -1;
+                                if (!lLocal && conf[rl]) ql = remoteSpin(0, x, w, rl);
+                                if (!rLocal && conf[K + rl]) qr = remoteSpin(1, x, w, rl);
+                                nb = (ql + qr + 2) >> 1;
                             }
-                            dE = P.twoDivM * qyx * (hx + real(2) * sum);
-                            dE -= qyx * real(ql + qr) * P.coef;
-                        } else {
-                            dE = real(2) * qyx * (hx + real(2) * sum);
+                            v -= P.scaleNb * real(2 * nb - 2);
                         }
-                        const real thr = (dE < real(0)) ? real(1) : expReal<real>(-dE * P.beta);
-                        const bool acc = thr > ux;
+                        const bool acc = (up ? v : -v) < lnu; /* exp(-dE beta) > u */
                         if (acc) {
-                            *word = wv ^ (1ull << bit);
+                            my32[w32] = wv ^ (1u << bit);
                             accC |= 1u << rl;
-                            if (up) sgnC |= 1u << rl;
+                            sgnC |= up << rl;
                             ++nAccepted;
                         }
                         if (publishes) {
-                            const unsigned long long rr = (unsigned long long)w * K + rl;
-                            const unsigned long long fv = ((P.roundBase + rr + 1ull) << 1) | (acc ? 1ull : 0ull);
-                            stRelaxed(myFlags + (rr % SW_FLAG_RING), fv);
-                            if (mirror0) stRelaxedSys(mirror0 + (rr % SW_FLAG_RING), fv);
-                            if (mirror1) stRelaxedSys(mirror1 + (rr % SW_FLAG_RING), fv);
+                            const unsigned long long fv = flagBase + (unsigned long long)(2 * rl) + (acc ? 1ull : 0ull);
+                            const int fs = (flagSlot + rl) % SW_FLAG_RING;
+                            stRelaxed(myFlags + fs, fv);
+                            if (mirror0) stRelaxedSys(mirror0 + fs, fv);
+                            if (mirror1) stRelaxedSys(mirror1 + fs, fv);
                         }
                     }
                     __syncwarp();
                 }
             }
+            const long long tLoop = clock64();
+            if (w + 1 < nW) chainHousekeeping(w + 1);
+            const long long tHk = clock64();
+            /* (x, -ln u, h) two windows ahead; reuses the ring slot of window w-1, which nobody reads any more */
+            prepWindow(w + 2, lane, 32);
+            __syncwarp();
+            const long long tPrep = clock64();
+            cycLoop += tLoop - tBusy0; cycHk += tHk - tLoop; cycPrep += tPrep - tHk;
             accP = accC; sgnP = sgnC; accC = 0; sgnC = 0;
+            busy += clock64() - tBusy0;
         }
-        {
-            const long long t0 = clock64();
-            __syncthreads();
-            if (lane == 0 && (warp == 0 || chainWarp)) barrierWait += clock64() - t0;
-        }
+        __syncthreads();
         /* new snapshot S_{w+1}; publish the edge trotters for the neighbouring CTAs */
         for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
         if (remote && w + 1 < nW) {
@@ -476,7 +518,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 int t = e ? T - 1 : 0;
                 const unsigned long long v = qcur[(size_t)t * NW + k];
                 const size_t off = (size_t)((w + 1) % SW_SNAP_SLOTS) * NW + k;
-                P.snapBits[(size_t)(y0 + t) * SW_SNAP_SLOTS * NW + off] = v;
+                sBits[(size_t)(y0 + t) * SW_SNAP_SLOTS * NW + off] = v;
                 if (ringSharded) {
                     if (y0 + t == 0 && P.peerSnapBits[0]) P.peerSnapBits[0][(size_t)(m + 1) * SW_SNAP_SLOTS * NW + off] = v;
                     if (y0 + t == m - 1 && P.peerSnapBits[1]) P.peerSnapBits[1][(size_t)m * SW_SNAP_SLOTS * NW + off] = v;
@@ -487,8 +529,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         __syncthreads();
         if (remote && w + 1 < nW && tid == 0) {
             const unsigned long long sv = P.snapBase + (unsigned long long)(w + 1);
-            stRelease(P.snapFlags + y0, sv);
-            if (T > 1) stRelease(P.snapFlags + y0 + T - 1, sv);
+            stRelease(sFlags + y0, sv);
+            if (T > 1) stRelease(sFlags + y0 + T - 1, sv);
             if (ringSharded) {
                 if (y0 == 0 && P.peerSnapFlags[0]) stReleaseSys(P.peerSnapFlags[0] + m + 1, sv);
                 if (y0 + T == m && P.peerSnapFlags[1]) stReleaseSys(P.peerSnapFlags[1] + m, sv);
@@ -504,7 +546,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             int w64, bit;
             spinBitPos(j, w64, bit);
             unsigned nib = (unsigned)(qcur[(size_t)r * NW + w64] >> bit) & 0xfu;
-            signed char *dst = P.q + (size_t)(y0 + r) * P.ldq + j;
+            signed char *dst = qBase + (size_t)(y0 + r) * P.ldq + j;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (j + e < N) dst[e] = ((nib >> e) & 1u) ? 1 : -1;
@@ -516,10 +558,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         if (lane == 0) {
             atomicAdd(P.stats, nAccepted);
             atomicAdd(P.stats + 1, nWaits);
-            atomicAdd(P.stats + 3, (unsigned long long)barrierWait); /* chain warp waiting for the dot warps */
+            atomicAdd(P.stats + 3, (unsigned long long)busy); /* chain warp: cycles spent replaying windows */
+            atomicAdd(P.stats + 4, (unsigned long long)cycLoop);
+            atomicAdd(P.stats + 5, (unsigned long long)cycHk);
+            atomicAdd(P.stats + 6, (unsigned long long)cycPrep);
         }
     }
-    if (warp == 0 && lane == 0 && P.stats) atomicAdd(P.stats + 2, (unsigned long long)barrierWait); /* dot warp 0 waiting */
+    if (warp == 0 && lane == 0 && P.stats) atomicAdd(P.stats + 2, (unsigned long long)busy); /* dot warp 0: cycles spent on dot products */
 }
 
 /* ---------------- small element-wise kernels ---------------- */
@@ -757,7 +802,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages, K).total;
     nWindows_ = (N_ + K - 1) / K;
     allocHandoff();
-    dStats_.alloc(dev_, 4);
+    dStats_.alloc(dev_, 8);
     launchCount_ = 0;
     CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(true, K_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
     CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(false, K_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
@@ -903,10 +948,14 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
         P.twoDivM = real(2.) / real(mAll);
         P.coef = std::log(std::tanh(G * beta / mAll)) / beta;
         P.beta = beta;
+        P.scaleA = beta * P.twoDivM;
+        P.scaleNb = beta * P.coef;
     } else { /* annealOneStep(kT, _) for SA: CUDADenseGraphAnnealer.cu:585-602 */
         P.twoDivM = real(2.);
         P.coef = real(0.);
         P.beta = real(1.) / G;
+        P.scaleA = real(2.) * P.beta;
+        P.scaleNb = real(0.);
     }
     P.chunkElems = chunkElems_; P.chunksPerRow = chunksPerRow_; P.stages = stages_; P.nw64 = nw64_; P.K = K_;
     HandoffLayout hl(m_, nw64_, ldq_);
@@ -1043,7 +1092,7 @@ template <class real> void B200DenseGraphAnnealer<real>::ringPushHalos() {
 }
 
 template <class real> void B200DenseGraphAnnealer<real>::getStats(unsigned long long *accepted, unsigned long long *waits) const {
-    unsigned long long h[4] = {0, 0, 0, 0};
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (dStats_.p) {
         dev_->d2h(h, dStats_.p, sizeof(h));
         dev_->synchronize();
@@ -1052,6 +1101,7 @@ template <class real> void B200DenseGraphAnnealer<real>::getStats(unsigned long 
     *waits = h[1];
     lastBarrierWaitDot_ = h[2];
     lastBarrierWaitChain_ = h[3];
+    if (getenv("SQAOD_B200_CHAIN_PROFILE")) fprintf(stderr, "chain cycles: loop %llu housekeeping %llu prep %llu\n", h[4], h[5], h[6]);
 }
 
 template class B200DenseGraphAnnealer<float>;

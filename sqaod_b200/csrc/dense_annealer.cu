@@ -69,7 +69,7 @@ template <class real> struct SweepParams {
 
 /* shared-memory carve-up, identical on host and device */
 template <class real> struct SweepSmem {
-    size_t ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, total;
+    size_t ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, counter, total;
     __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K) {
         size_t o = 0;
         ring = o; o += (size_t)SW_DOT_WARPS * stages * chunkElems * sizeof(real);
@@ -87,6 +87,7 @@ template <class real> struct SweepSmem {
         hs = o; o += (size_t)3 * T * K * sizeof(real);
         xn = o; o += (size_t)2 * 3 * K * 4;
         conf = o; o += (size_t)2 * K * 4;
+        counter = o; o += 16;
         total = (o + 127) & ~(size_t)127;
     }
 };
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     real *hs = reinterpret_cast<real *>(smem + L.hs);
     int *xn = reinterpret_cast<int *>(smem + L.xn);          /* [2 sides][3][K] */
     uint32_t *conf = reinterpret_cast<uint32_t *>(smem + L.conf); /* [2][K] */
+    unsigned int *taskCounter = reinterpret_cast<unsigned int *>(smem + L.counter);
 
     /* ring topology: local index l <-> global trotter (yOff + l) mod mRing */
     const int mRing = P.mRing, yOff = P.yOff;
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     for (int i = tid; i < maxT * NW; i += SW_THREADS) qcur[i] = 0ull;
     for (int i = tid; i < 2 * NW; i += SW_THREADS) nbsnap[i] = 0ull;
     if (tid == 0) {
+        *taskCounter = 0u;
         for (int i = 0; i < SW_DOT_WARPS * S; ++i) mbarInit(&bars[i], 1);
         mbarInitFence();
     }
@@ -262,8 +265,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     __syncthreads();
 
     /* ---------------- dot warps: per-warp TMA ring state ---------------- */
-    /* task = (window w, id = rl * T + t); warp d owns ids d, d + 8, ... of every window */
-    int iw = 0, iid = warp, ic = 0, ix = 0; /* issue cursor (lane 0) */
+    /* task g = w * (K*T) + id, id = rl * T + t.  Tasks are CLAIMED dynamically (shared counter) by whichever dot warp is about to
+     * issue a new row, so a warp slowed down by HBM/L2 queueing simply takes fewer rows: with a static split every window
+     * waited for the unluckiest of 16 warps (35 % of all warp samples sat at the window barrier).  Claims are monotone,
+     * hence in window order; a warp prefetches at most its next row across a window boundary and consumes it after the barrier. */
+    const int TPW = K * T;                                   /* tasks per full window */
+    const int totalTasks = (nW - 1) * TPW + roundsIn(nW - 1) * T;
+    int ic = 0, ix = 0;                     /* issue cursor (lane 0): chunk within the row being issued, its row index */
+    int fifo0 = -1, fifo1 = -1;             /* lane 0: claimed tasks not yet consumed (oldest first) */
     int iStage = 0;                         /* ring slot the next issue goes to */
     int cStage = 0;                         /* ring slot the next consume reads, and its mbarrier phase parity */
     uint32_t cParity = 0;
@@ -271,15 +280,15 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     uint64_t *myBars = bars + warp * S;
     real *myRing = ring + (size_t)warp * S * CH;
 
-    auto skipEmptyWindows = [&](int &w, int &id) {
-        while (w < nW && id >= roundsIn(w) * T) { ++w; id = warp; }
-    };
     auto issueNext = [&]() { /* lane 0 of a dot warp */
         if (issueDone) return;
         if (ic == 0) {
-            skipEmptyWindows(iw, iid);
-            if (iw >= nW) { issueDone = true; return; }
-            int t = iid % T, rl = iid / T;
+            if (fifo1 >= 0) return; /* two rows pending already (rows shorter than the ring): claim again after the next pop */
+            const int g = (int)atomicAdd(taskCounter, 1u);
+            if (g >= totalTasks) { issueDone = true; return; }
+            if (fifo0 < 0) fifo0 = g; else fifo1 = g;
+            const int iw = g / TPW, iid = g - iw * TPW;
+            const int t = iid % T, rl = iid / T;
             Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(iw * K + rl), (uint32_t)gOf(y0 + t));
             ix = (int)(p.w[0] % (uint32_t)N);
         }
@@ -288,15 +297,18 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         mbarArriveExpectTx(&myBars[iStage], bytes);
         tmaLoad1D(myRing + (size_t)iStage * CH, P.J + (size_t)ix * P.ldJ + (size_t)ic * CH, bytes, &myBars[iStage]);
         if (++iStage == S) iStage = 0;
-        if (++ic == CPR) { ic = 0; iid += SW_DOT_WARPS; }
+        if (++ic == CPR) ic = 0;
     };
     if (warp < SW_DOT_WARPS && lane == 0)
         for (int s = 0; s < S; ++s) issueNext();
 
     /* consume every task this warp owns in window w; results go to buffer w & 1 */
     auto dotWindow = [&](int w) {
-        const int Kw = roundsIn(w), buf = w & 1;
-        for (int id = warp; id < Kw * T; id += SW_DOT_WARPS) {
+        const int buf = w & 1;
+        for (;;) {
+            const int g = __shfl_sync(0xffffffffu, fifo0, 0); /* oldest row this warp has claimed and not yet reduced */
+            if (g < 0 || g / TPW != w) break;                 /* nothing left, or it belongs to a later window */
+            const int id = g - w * TPW;
             const int t = id % T, rl = id / T;
             /* column whose J[x][col] this lane must pick up: lane j < K -> round j of window w-1, else round j-K of w */
             int px = -1;
@@ -328,7 +340,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 }
                 if (px >= c0 && px < c0 + (groups << 7)) crossv = buf_[px - c0];
                 __syncwarp();
-                if (lane == 0) issueNext();
+                if (lane == 0) {
+                    if (c == CPR - 1) { fifo0 = fifo1; fifo1 = -1; } /* this row is done: make room before claiming */
+                    issueNext();
+                }
                 if (++cStage == S) { cStage = 0; cParity ^= 1u; }
             }
             real s = warpSum((a0 + a1) + (a2 + a3));

@@ -1116,7 +1116,6 @@ template <class real> void B200DenseGraphAnnealer<real>::getStats(unsigned long 
     *waits = h[1];
     lastBarrierWaitDot_ = h[2];
     lastBarrierWaitChain_ = h[3];
-    if (getenv("SQAOD_B200_CHAIN_PROFILE")) fprintf(stderr, "chain cycles: loop %llu housekeeping %llu prep %llu\n", h[4], h[5], h[6]);
 }
 
 template class B200DenseGraphAnnealer<float>;

@@ -93,6 +93,9 @@ CHAIN_CASES = [
     (300, 296, 'coloring', 1),     # T = 2 everywhere, every CTA has remote neighbours
     (1000, 32, 'coloring', 1),
     (2100, 12, 'coloring', 1),     # more than one 2048-spin super-block, several chunks per row
+    (64, 512, 'coloring', 2),      # the C2 trotter layout: 148 CTAs with 4 or 3 trotters each
+    (128, 601, 'coloring', 1),     # 5 / 4 trotters per CTA, odd ring
+    (4500, 6, 'coloring', 1),      # rows longer than a super-block, partial last chunk
     (24, 1, 'sa_naive', 5),
     (50, 9, 'sa_naive', 3),
 ]

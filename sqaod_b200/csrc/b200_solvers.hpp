@@ -69,6 +69,7 @@ public:
     void getSpinsRaw(signed char *q) const;
     void getStats(unsigned long long *accepted, unsigned long long *waits) const;
     void getBarrierStats(unsigned long long *dot, unsigned long long *chain) const { *dot = lastBarrierWaitDot_; *chain = lastBarrierWaitChain_; }
+    void getCounters(unsigned long long out[8]) const; /* raw sweep counters, see SweepParams::stats */
     int numTrotters() const { return m_; }
     /* replica batch: R independent replicas of the problem (seed + r) annealed side by side; spin / energy rows are [r][y] */
     void setNumReplicas(int n);

@@ -207,6 +207,7 @@ int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, 
     DISPATCH(dtype, { unsigned long long a, w; DGAX(real)->getStats(&a, &w); DGAX(real)->getBarrierStats(dot, chain); })
     SQB_CATCH
 }
+int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getCounters(out8)) SQB_CATCH }
 int sqb_dg_annealer_get_spins(sqb_handle ann, signed char *q, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getSpinsRaw(q)) SQB_CATCH }
 
 int sqb_dg_annealer_set_num_replicas(sqb_handle ann, int n, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->setNumReplicas(n)) SQB_CATCH }

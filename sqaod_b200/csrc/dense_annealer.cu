@@ -38,7 +38,8 @@
 
 namespace sqb {
 
-enum { SW_MAX_K = 16, SW_DOT_WARPS = 16, SW_THREADS = (SW_DOT_WARPS + 1) * 32, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4 };
+enum { SW_MAX_K = 16, SW_DOT_WARPS = 12, SW_THREADS = 512, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4,
+       SW_CHAIN_WARP = 0, SW_HELPER_WARP = 4, SW_PREP_WARP = 8 /* warp 12 is a spare; the dot warps are those with warp & 3 != 0 */ };
 
 template <class real> struct SweepParams {
     const real *J;
@@ -69,14 +70,14 @@ template <class real> struct SweepParams {
 
 /* shared-memory carve-up, identical on host and device */
 template <class real> struct SweepSmem {
-    size_t ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, counter, total;
+    size_t ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, confAny, accLog, counter, total;
     __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K) {
         size_t o = 0;
         ring = o; o += (size_t)SW_DOT_WARPS * stages * chunkElems * sizeof(real);
         bars = o; o += (size_t)SW_DOT_WARPS * stages * 8;
         qcur = o; o += (size_t)T * nw64 * 8;
         qsnap = o; o += (size_t)T * nw64 * 8;
-        nbsnap = o; o += (size_t)2 * nw64 * 8;
+        nbsnap = o; o += (size_t)2 * 2 * nw64 * 8;
         dots = o; o += (size_t)2 * T * K * sizeof(real);
         o = (o + 15) & ~(size_t)15;
         cross = o; o += (size_t)2 * T * K * (2 * K) * sizeof(real);
@@ -86,7 +87,10 @@ template <class real> struct SweepSmem {
         us = o; o += (size_t)3 * T * K * sizeof(real);
         hs = o; o += (size_t)3 * T * K * sizeof(real);
         xn = o; o += (size_t)2 * 3 * K * 4;
-        conf = o; o += (size_t)2 * K * 4;
+        conf = o; o += (size_t)2 * 2 * K * 4;
+        confAny = o; o += 16;
+        accLog = o; o += (size_t)2 * T * 4;
+        o = (o + 15) & ~(size_t)15;
         counter = o; o += 16;
         total = (o + 127) & ~(size_t)127;
     }
@@ -147,6 +151,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     unsigned long long *const sFlags = P.snapFlags + handoffOff;
     unsigned long long *const sBits = P.snapBits + handoffOff;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    /* warp roles.  Warps are spread over the SM's four schedulers by (warp & 3): scheduler 0 is kept for the latency-bound
+     * accept chain and its helpers, the twelve streaming dot warps share the other three. */
+    const bool dotWarp = (warp & 3) != 0;
+    const int dw = (warp >> 2) * 3 + (warp & 3) - 1; /* dot warp index 0..11 */
+    const bool chainWarp = (warp == SW_CHAIN_WARP), helperWarp = (warp == SW_HELPER_WARP), prepWarp = (warp == SW_PREP_WARP);
     const int N = P.N, m = P.m;
     const int G = gridDim.x, cta = blockIdx.x;
     const int baseT = m / G, remT = m % G;
@@ -162,7 +171,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
     unsigned long long *qcur = reinterpret_cast<unsigned long long *>(smem + L.qcur);
     unsigned long long *qsnap = reinterpret_cast<unsigned long long *>(smem + L.qsnap);
-    unsigned long long *nbsnap = reinterpret_cast<unsigned long long *>(smem + L.nbsnap);
+    unsigned long long *nbsnap = reinterpret_cast<unsigned long long *>(smem + L.nbsnap); /* [2 buffers][2 sides][NW] */
     real *dots = reinterpret_cast<real *>(smem + L.dots);    /* [2][maxT][K] */
     real *cross = reinterpret_cast<real *>(smem + L.cross);  /* [2][maxT][K][2K] */
     int *xs = reinterpret_cast<int *>(smem + L.xs);          /* [3][maxT][K] */
@@ -170,7 +179,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     real *us = reinterpret_cast<real *>(smem + L.us);
     real *hs = reinterpret_cast<real *>(smem + L.hs);
     int *xn = reinterpret_cast<int *>(smem + L.xn);          /* [2 sides][3][K] */
-    uint32_t *conf = reinterpret_cast<uint32_t *>(smem + L.conf); /* [2][K] */
+    uint32_t *conf = reinterpret_cast<uint32_t *>(smem + L.conf);       /* [2 buffers][2 sides][K] */
+    uint32_t *confAny = reinterpret_cast<uint32_t *>(smem + L.confAny); /* [2 buffers][2 sides]: rounds with a non-empty mask */
+    uint32_t *accLog = reinterpret_cast<uint32_t *>(smem + L.accLog);   /* [2 buffers][maxT]: accept bits of a window */
     unsigned int *taskCounter = reinterpret_cast<unsigned int *>(smem + L.counter);
 
     /* ring topology: local index l <-> global trotter (yOff + l) mod mRing */
@@ -178,10 +189,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     const bool ringSharded = (mRing != m);
     auto gOf = [&](int l) { int g = yOff + l; return g >= mRing ? g - mRing : g; };
     auto slotOf = [&](int g) { /* hand-off slot of global trotter g: local index, or m / m+1 for the foreign neighbours */
-        int d = g - yOff;
-        if (d < 0) d += mRing;
-        if (d < m) return d;
-        return (d == mRing - 1) ? m : m + 1;
+        int dd = g - yOff;
+        if (dd < 0) dd += mRing;
+        if (dd < m) return dd;
+        return (dd == mRing - 1) ? m : m + 1;
     };
     /* trotters of other CTAs (or GPUs) adjacent to this CTA's range (SQA only); global indices */
     const int gFirst = gOf(y0), gLast = gOf(y0 + T - 1);
@@ -192,7 +203,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
 
     auto roundsIn = [&](int w) { return min(K, N - w * K); };
 
-    /* (x, u, h[x]) of every attempt of window w for the owned trotters, plus the remote neighbours' x */
+    /* (x, -ln u, h[x]) of every attempt of window w for the owned trotters, plus the remote neighbours' x */
     auto prepWindow = [&](int w, int t0, int nthr) {
         if (w >= nW) return;
         const int Kw = roundsIn(w), slot = w % 3;
@@ -219,9 +230,48 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         }
     };
 
-    /* ---------------- setup ---------------- */
+    unsigned long long nWaits = 0;
+
+    /* helper warp: what chain window wn needs from the neighbouring CTAs -- their snapshot S_{wn-1} and, per attempt of
+     * my edge trotters, the mask of neighbour attempts (previous + current window) that hit the same spin index.
+     * Written to buffer wn & 1 while the chain replays window wn - 1 out of the other buffer. */
+    auto neighbourWindow = [&](int wn) {
+        if (!remote) return;
+        const int Kn = roundsIn(wn), slotN = wn % 3, bN = wn & 1;
+        if (wn >= 2) {
+            for (int side = 0; side < 2; ++side) {
+                const int sl = side ? slotR : slotL;
+                if (lane == 0) {
+                    const unsigned long long want = P.snapBase + (unsigned long long)(wn - 1);
+                    if (ringSharded) { while (ldAcquireSys(sFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
+                    else { while (ldAcquire(sFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
+                }
+                __syncwarp();
+                const unsigned long long *src = sBits + ((size_t)sl * SW_SNAP_SLOTS + ((wn - 1) % SW_SNAP_SLOTS)) * NW;
+                unsigned long long *dst = nbsnap + (size_t)(bN * 2 + side) * NW;
+                for (int i = lane; i < NW; i += 32) dst[i] = __ldcg(src + i);
+            }
+        }
+        for (int side = 0; side < 2; ++side) {
+            int nbx = -1;
+            if (lane < K) { if (wn > 0) nbx = xn[(side * 3 + (wn - 1) % 3) * K + lane]; }
+            else if (lane < 2 * K && lane - K < Kn) nbx = xn[(side * 3 + slotN) * K + (lane - K)];
+            const int tEdge = side ? T - 1 : 0;
+            uint32_t any = 0;
+            for (int rl = 0; rl < Kn; ++rl) {
+                int xe = xs[(slotN * maxT + tEdge) * K + rl];
+                uint32_t hit = __ballot_sync(0xffffffffu, nbx == xe);
+                if (lane == 0) conf[(bN * 2 + side) * K + rl] = hit;
+                any |= (hit ? 1u : 0u) << rl;
+            }
+            if (lane == 0) confAny[bN * 2 + side] = any;
+        }
+        __syncwarp();
+    };
+
+    /* ---------------- setup (all warps) ---------------- */
     for (int i = tid; i < maxT * NW; i += SW_THREADS) qcur[i] = 0ull;
-    for (int i = tid; i < 2 * NW; i += SW_THREADS) nbsnap[i] = 0ull;
+    for (int i = tid; i < 4 * NW; i += SW_THREADS) nbsnap[i] = 0ull;
     if (tid == 0) {
         *taskCounter = 0u;
         for (int i = 0; i < SW_DOT_WARPS * S; ++i) mbarInit(&bars[i], 1);
@@ -262,13 +312,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     prepWindow(1, tid, SW_THREADS);
     __syncthreads();
     for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
-    __syncthreads();
+    for (int i = tid; i < 2 * NW; i += SW_THREADS) nbsnap[2 * NW + i] = nbsnap[i]; /* windows 0 and 1 both start from S_0 */
+    if (helperWarp) neighbourWindow(0);
 
     /* ---------------- dot warps: per-warp TMA ring state ---------------- */
     /* task g = w * (K*T) + id, id = rl * T + t.  Tasks are CLAIMED dynamically (shared counter) by whichever dot warp is about to
-     * issue a new row, so a warp slowed down by HBM/L2 queueing simply takes fewer rows: with a static split every window
-     * waited for the unluckiest of 16 warps (35 % of all warp samples sat at the window barrier).  Claims are monotone,
-     * hence in window order; a warp prefetches at most its next row across a window boundary and consumes it after the barrier. */
+     * issue a new row, so a warp slowed down by HBM/L2 queueing simply takes fewer rows.  Claims are monotone, hence in
+     * window order; a warp prefetches at most its next row across a window boundary and consumes it after the barrier. */
     const int TPW = K * T;                                   /* tasks per full window */
     const int totalTasks = (nW - 1) * TPW + roundsIn(nW - 1) * T;
     int ic = 0, ix = 0;                     /* issue cursor (lane 0): chunk within the row being issued, its row index */
@@ -277,8 +327,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     int cStage = 0;                         /* ring slot the next consume reads, and its mbarrier phase parity */
     uint32_t cParity = 0;
     bool issueDone = false;
-    uint64_t *myBars = bars + warp * S;
-    real *myRing = ring + (size_t)warp * S * CH;
+    uint64_t *myBars = bars + (dotWarp ? dw : 0) * S;
+    real *myRing = ring + (size_t)(dotWarp ? dw : 0) * S * CH;
 
     auto issueNext = [&]() { /* lane 0 of a dot warp */
         if (issueDone) return;
@@ -299,7 +349,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         if (++iStage == S) iStage = 0;
         if (++ic == CPR) ic = 0;
     };
-    if (warp < SW_DOT_WARPS && lane == 0)
+    if (dotWarp && lane == 0)
         for (int s = 0; s < S; ++s) issueNext();
 
     /* consume every task this warp owns in window w; results go to buffer w & 1 */
@@ -353,203 +403,262 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     };
 
     /* prologue: dot products of window 0 (against the launch state) */
-    if (warp < SW_DOT_WARPS) dotWindow(0);
+    __syncthreads();
+    if (dotWarp) dotWindow(0);
     __syncthreads();
 
-    /* ---------------- chain warp state ---------------- */
-    const bool chainWarp = (warp == SW_DOT_WARPS);
-    const bool active = chainWarp && (lane < T);
-    const int y = y0 + lane;                 /* local index */
-    const int gy = gOf(lane < T ? y : y0);   /* global trotter */
-    const int myPhase = sweepPhase(gy, mRing);
-    const int yl = slotOf(gy == 0 ? mRing - 1 : gy - 1), yr = slotOf(gy == mRing - 1 ? 0 : gy + 1); /* slots of the neighbours */
-    const bool lLocal = (yl >= y0 && yl < y0 + T), rLocal = (yr >= y0 && yr < y0 + T);
-    uint32_t accP = 0, sgnP = 0, accC = 0, sgnC = 0;
-    /* rows the chain reads for this lane: its own, and its neighbours' (current state when the neighbour lives in this
-     * CTA, else the published snapshot of side 0 / 1) */
-    unsigned long long *myRow = qcur + (size_t)(lane < T ? lane : 0) * NW;
-    const unsigned long long *leftRow = lLocal ? qcur + (size_t)(yl - y0) * NW : nbsnap;
-    const unsigned long long *rightRow = rLocal ? qcur + (size_t)(yr - y0) * NW : nbsnap + NW;
-    const bool publishes = remote && active && (lane == 0 || lane == T - 1);
-    uint32_t *my32 = reinterpret_cast<uint32_t *>(myRow);
-    const uint32_t *left32 = reinterpret_cast<const uint32_t *>(leftRow), *right32 = reinterpret_cast<const uint32_t *>(rightRow);
-    const bool remoteMask = remote && (!lLocal || !rLocal);
-    unsigned long long *myFlags = aFlags + (size_t)(active ? y : 0) * SW_FLAG_RING;
-    /* the first / last trotter of a sharded ring also publishes into the neighbouring GPU's arrays */
-    unsigned long long *mirror0 = (ringSharded && active && y == 0 && P.peerFlags[0]) ? P.peerFlags[0] + (size_t)(m + 1) * SW_FLAG_RING : NULL;
-    unsigned long long *mirror1 = (ringSharded && active && y == m - 1 && P.peerFlags[1]) ? P.peerFlags[1] + (size_t)m * SW_FLAG_RING : NULL;
-    unsigned long long nAccepted = 0, nWaits = 0;
-
-    /* spin of a trotter owned by another CTA: published snapshot, corrected by the accept bits of the neighbour's
-     * attempts that hit the same spin index since the snapshot */
-    auto remoteSpin = [&](int side, int x, int w, int rl) -> int {
-        int v = spinAt(nbsnap + (size_t)side * NW, x);
-        uint32_t mask = conf[side * K + rl];
-        if (mask) {
-            const int yn = side ? yRight : yLeft;
-            const int nbPhase = sweepPhase(yn, mRing);
-            uint32_t vis = (w > 0 ? ((1u << K) - 1u) : 0u) | (((1u << rl) - 1u) << K) | ((nbPhase < myPhase) ? (1u << (K + rl)) : 0u);
-            mask &= vis;
-            while (mask) {
-                int j = __ffs(mask) - 1;
-                mask &= mask - 1;
-                long long rr = (long long)w * K + (j - K); /* j < K: previous window */
-                const unsigned long long want = P.roundBase + (unsigned long long)rr + 1ull;
-                const unsigned long long *f = aFlags + (size_t)(side ? slotR : slotL) * SW_FLAG_RING + (rr % SW_FLAG_RING);
-                /* the flag word carries its own payload (tag, accept bit): relaxed accesses are enough */
-                unsigned long long got = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f);
-                while ((got >> 1) != want) { ++nWaits; __nanosleep(20); got = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f); }
-                if (got & 1ull) v = -v;
-            }
-        }
-        return v;
+    /* Window protocol (w = 0 .. nW-1), all hand-offs inside the CTA through two barriers:
+     *   chain  : fold window w-1's flips into dots[w], replay window w on qcur, log its accept bits            | A
+     *   helper : apply window w-1's flips to qsnap (= S_w)   | B | publish S_w, fetch neighbours' S_w, masks   | A
+     *   prep   :                                              | B | (x, -ln u, h) of window w+2                  | A
+     *   dot    :                                              | B | dot products of window w+1 against S_w      | A
+     * so the chain never waits for a copy or a publication, only for the dot products of its next window. */
+    auto barA = [&]() { namedBarSync(1, SW_THREADS); };
+    auto barB = [&]() { namedBarSync(2, SW_THREADS - 64); }; /* everyone but the chain warp and the spare warp */
+    long long busy = 0, cycA = 0, cycB = 0;
+    auto touchSmem = [&]() { /* BAR.SYNC blocks lazily: touch shared memory so that waiting is not booked as work */
+        unsigned int dummy;
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(dummy) : "r"(smemAddr(taskCounter)) : "memory");
     };
 
-    /* what chain window wn needs from the neighbouring CTAs: their snapshot S_{wn-1} and the masks of the neighbour attempts
-     * (previous + current window) that hit the spin index of my attempt rl */
-    auto chainHousekeeping = [&](int wn) __attribute__((always_inline)) {
-        if (!remote) return;
-        const int Kn = roundsIn(wn), slotN = wn % 3;
-        if (wn >= 2) {
-            for (int side = 0; side < 2; ++side) {
-                const int sl = side ? slotR : slotL;
+    if (dotWarp) {
+        for (int w = 0; w < nW; ++w) {
+            barB();
+            touchSmem();
+            const long long t0 = clock64();
+            if (w + 1 < nW) dotWindow(w + 1);
+            busy += clock64() - t0;
+            barA();
+        }
+    } else if (helperWarp) {
+        uint32_t *qsnap32 = reinterpret_cast<uint32_t *>(qsnap);
+        for (int w = 0; w < nW; ++w) {
+            touchSmem();
+            const long long t0 = clock64();
+            if (w > 0 && lane < T) { /* S_w = S_{w-1} with the accepted flips of window w-1 */
+                uint32_t bitsAcc = accLog[((w - 1) & 1) * maxT + lane];
+                const int *xbRow = xb + (((w - 1) % 3) * maxT + lane) * K;
+                uint32_t *row = qsnap32 + (size_t)lane * 2 * NW;
+                while (bitsAcc) {
+                    const int rl = __ffs(bitsAcc) - 1;
+                    bitsAcc &= bitsAcc - 1;
+                    const int xbv = xbRow[rl];
+                    row[xbv >> 5] ^= 1u << (xbv & 31);
+                }
+            }
+            __syncwarp();
+            barB();
+            if (remote && w >= 1) { /* publish the edge trotters' S_w for the neighbouring CTAs */
+                const int nEdge = (T > 1) ? 2 : 1;
+                for (int i = lane; i < nEdge * NW; i += 32) {
+                    int e = i / NW, k = i % NW;
+                    int t = e ? T - 1 : 0;
+                    const unsigned long long v = qsnap[(size_t)t * NW + k];
+                    const size_t off = (size_t)(w % SW_SNAP_SLOTS) * NW + k;
+                    sBits[(size_t)(y0 + t) * SW_SNAP_SLOTS * NW + off] = v;
+                    if (ringSharded) {
+                        if (y0 + t == 0 && P.peerSnapBits[0]) P.peerSnapBits[0][(size_t)(m + 1) * SW_SNAP_SLOTS * NW + off] = v;
+                        if (y0 + t == m - 1 && P.peerSnapBits[1]) P.peerSnapBits[1][(size_t)m * SW_SNAP_SLOTS * NW + off] = v;
+                    }
+                }
+                if (ringSharded) __threadfence_system(); else __threadfence();
+                __syncwarp();
                 if (lane == 0) {
-                    const unsigned long long want = P.snapBase + (unsigned long long)(wn - 1);
-                    if (ringSharded) { while (ldAcquireSys(sFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
-                    else { while (ldAcquire(sFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
+                    const unsigned long long sv = P.snapBase + (unsigned long long)w;
+                    stRelease(sFlags + y0, sv);
+                    if (T > 1) stRelease(sFlags + y0 + T - 1, sv);
+                    if (ringSharded) {
+                        if (y0 == 0 && P.peerSnapFlags[0]) stReleaseSys(P.peerSnapFlags[0] + m + 1, sv);
+                        if (y0 + T == m && P.peerSnapFlags[1]) stReleaseSys(P.peerSnapFlags[1] + m, sv);
+                    }
+                }
+            }
+            if (w + 1 < nW) neighbourWindow(w + 1);
+            busy += clock64() - t0;
+            barA();
+        }
+    } else if (prepWarp) {
+        for (int w = 0; w < nW; ++w) {
+            barB();
+            touchSmem();
+            const long long t0 = clock64();
+            prepWindow(w + 2, lane, 32); /* reuses the table slot of window w-1, which the helper has just finished with */
+            busy += clock64() - t0;
+            barA();
+        }
+    } else if (!chainWarp) {
+        for (int w = 0; w < nW; ++w) barA(); /* spare warp: keeps the accept chain's scheduler free */
+    } else {
+        /* ---------------- the accept chain: lane = trotter ---------------- */
+        const bool active = (lane < T);
+        const int tl = active ? lane : 0;
+        const int gy = gOf(y0 + tl);             /* global trotter */
+        const int myPhase = active ? sweepPhase(gy, mRing) : -1;
+        const bool oddRing = (mRing & 1) != 0;
+        const int yl = slotOf(gy == 0 ? mRing - 1 : gy - 1), yr = slotOf(gy == mRing - 1 ? 0 : gy + 1); /* slots of the neighbours */
+        const bool lLocal = (yl >= y0 && yl < y0 + T), rLocal = (yr >= y0 && yr < y0 + T);
+        const bool remoteLane = remote && active && (!lLocal || !rLocal);
+        const bool publishes = remote && active && (lane == 0 || lane == T - 1);
+        const uint32_t rowBytes = (uint32_t)NW * 8u;
+        const uint32_t aMy = smemAddr(qcur) + (uint32_t)tl * rowBytes;
+        const uint32_t aLeftLocal = smemAddr(qcur) + (uint32_t)(lLocal ? yl - y0 : 0) * rowBytes;
+        const uint32_t aRightLocal = smemAddr(qcur) + (uint32_t)(rLocal ? yr - y0 : 0) * rowBytes;
+        const uint32_t aNb = smemAddr(nbsnap), aDots = smemAddr(dots), aCross = smemAddr(cross), aXb = smemAddr(xb), aUs = smemAddr(us);
+        unsigned long long *myFlags = aFlags + (size_t)(y0 + tl) * SW_FLAG_RING;
+        /* the first / last trotter of a sharded ring also publishes into the neighbouring GPU's arrays */
+        unsigned long long *mirror0 = (ringSharded && active && y0 + lane == 0 && P.peerFlags[0]) ? P.peerFlags[0] + (size_t)(m + 1) * SW_FLAG_RING : NULL;
+        unsigned long long *mirror1 = (ringSharded && active && y0 + lane == m - 1 && P.peerFlags[1]) ? P.peerFlags[1] + (size_t)m * SW_FLAG_RING : NULL;
+        const real corrScale = real(-4) * P.scaleA; /* a flip of spin x' accepted since the snapshot changes sum by -2 q_old J[x][x'] */
+        const real nbScale2 = real(2) * P.scaleNb;
+        uint32_t accP = 0, sgnP = 0;
+        unsigned long long nAccepted = 0;
+
+        for (int w = 0; w < nW; ++w) {
+            touchSmem();
+            const long long t0 = clock64();
+            const int Kw = roundsIn(w), buf = w & 1, slot = w % 3;
+            const unsigned long long *nbRows = nbsnap + (size_t)buf * 2 * NW;
+            const uint32_t *confW = conf + buf * 2 * K;
+
+            /* spin of a trotter owned by another CTA: published snapshot, corrected by the accept bits of the neighbour's
+             * attempts that hit the same spin index since the snapshot */
+            auto remoteSpin = [&](int side, int x, int rl) -> int {
+                int v = spinAt(nbRows + (size_t)side * NW, x);
+                uint32_t mask = confW[side * K + rl];
+                if (mask) {
+                    const int yn = side ? yRight : yLeft;
+                    const int nbPhase = sweepPhase(yn, mRing);
+                    uint32_t vis = (w > 0 ? ((1u << K) - 1u) : 0u) | (((1u << rl) - 1u) << K) | ((nbPhase < myPhase) ? (1u << (K + rl)) : 0u);
+                    mask &= vis;
+                    while (mask) {
+                        int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        long long rr = (long long)w * K + (j - K); /* j < K: previous window */
+                        const unsigned long long want = P.roundBase + (unsigned long long)rr + 1ull;
+                        const unsigned long long *f = aFlags + (size_t)(side ? slotR : slotL) * SW_FLAG_RING + (rr % SW_FLAG_RING);
+                        /* the flag word carries its own payload (tag, accept bit): relaxed accesses are enough */
+                        unsigned long long got = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f);
+                        while ((got >> 1) != want) { ++nWaits; __nanosleep(20); got = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f); }
+                        if (got & 1ull) v = -v;
+                    }
+                }
+                return v;
+            };
+
+            /* 1. fold the flips of window w-1 (known since the last barrier) into the snapshot dot products of window w:
+             *    one (trotter, round) item per lane, so this is off the serial path */
+            if (__any_sync(0xffffffffu, accP != 0u)) {
+                for (int i0 = 0; i0 < T * K; i0 += 32) {
+                    const int i = i0 + lane;
+                    const int t = min(i / K, T - 1), rl = i % K;
+                    uint32_t ev = __shfl_sync(0xffffffffu, accP, t);
+                    const uint32_t sg = __shfl_sync(0xffffffffu, sgnP, t);
+                    if (i < T * K && rl < Kw && ev) {
+                        const uint32_t aV = aDots + (uint32_t)(((buf * maxT + t) * K + rl) * sizeof(real));
+                        const uint32_t aC = aCross + (uint32_t)((((buf * maxT + t) * K + rl) * (2 * K)) * sizeof(real));
+                        real v, c;
+                        ldsReal(aV, v);
+                        do {
+                            const int j = __ffs(ev) - 1;
+                            ev &= ev - 1;
+                            ldsReal(aC + (uint32_t)(j * sizeof(real)), c);
+                            v += (((sg >> j) & 1u) ? corrScale : -corrScale) * c;
+                        } while (ev);
+                        stsReal(aV, v);
+                    }
                 }
                 __syncwarp();
-                const unsigned long long *src = sBits + ((size_t)sl * SW_SNAP_SLOTS + ((wn - 1) % SW_SNAP_SLOTS)) * NW;
-                for (int i = lane; i < NW; i += 32) nbsnap[(size_t)side * NW + i] = __ldcg(src + i);
             }
-        }
-        for (int side = 0; side < 2; ++side) {
-            int nbx = -1;
-            if (lane < K) { if (wn > 0) nbx = xn[(side * 3 + (wn - 1) % 3) * K + lane]; }
-            else if (lane < 2 * K && lane - K < Kn) nbx = xn[(side * 3 + slotN) * K + (lane - K)];
-            const int tEdge = side ? T - 1 : 0;
-            for (int rl = 0; rl < Kn; ++rl) {
-                int xe = xs[(slotN * maxT + tEdge) * K + rl];
-                uint32_t hit = __ballot_sync(0xffffffffu, nbx == xe);
-                if (lane == 0) conf[side * K + rl] = hit;
-            }
-        }
-        __syncwarp();
-    };
-    if (chainWarp) chainHousekeeping(0);
 
-    long long cycLoop = 0, cycHk = 0, cycPrep = 0;
-    long long busy = 0; /* cycles lane 0 of this warp spent working inside the windows (dot warp 0 and the chain warp report it) */
-    for (int w = 0; w < nW; ++w) {
-        /* BAR.SYNC blocks lazily (at the next use of barrier-protected state): touch shared memory before reading the clock so
-         * that the time spent waiting at the previous barrier is not booked as work */
-        { unsigned int dummy; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(dummy) : "r"(smemAddr(conf)) : "memory"); }
-        const long long tBusy0 = clock64();
-        if (warp < SW_DOT_WARPS) {
-            if (w + 1 < nW) dotWindow(w + 1);
-            busy += clock64() - tBusy0;
-        } else {
-            /* ---- chain warp: replay window w, then prepare what window w+1 needs while the dot warps are still busy ---- */
-            const int Kw = roundsIn(w), buf = w & 1, slot = w % 3;
-            const real *dotRow = dots + (buf * maxT + (lane < T ? lane : 0)) * K;
-            const int tabBase = (slot * maxT + (lane < T ? lane : 0)) * K;
-            const real corrScale = real(-4) * P.scaleA; /* a flip of spin x' accepted since the snapshot changes sum by -2 q_old J[x][x'] */
+            /* 2. replay.  Per round: a phase-independent part (tables, repair with this window's own flips) for all lanes,
+             *    then the state-dependent core once per phase of the reference order (even y, [y = m-1 of an odd ring], odd y) */
+            const uint32_t aLeft = lLocal ? aLeftLocal : aNb + (uint32_t)(buf * 2) * rowBytes;
+            const uint32_t aRight = rLocal ? aRightLocal : aNb + (uint32_t)(buf * 2 + 1) * rowBytes;
+            uint32_t cmask = 0; /* rounds in which a neighbour owned by another CTA attempts the same spin index */
+            if (remoteLane) cmask = (lLocal ? 0u : confAny[buf * 2]) | (rLocal ? 0u : confAny[buf * 2 + 1]);
+            uint32_t pXb = aXb + (uint32_t)(((slot * maxT + tl) * K) * 4);
+            uint32_t pUs = aUs + (uint32_t)(((slot * maxT + tl) * K) * sizeof(real));
+            uint32_t pDot = aDots + (uint32_t)(((buf * maxT + tl) * K) * sizeof(real));
+            uint32_t pCr = aCross + (uint32_t)((((buf * maxT + tl) * K) * (2 * K) + K) * sizeof(real)); /* this window's columns */
+            const int tabBase = (slot * maxT + tl) * K;
             const unsigned long long flagBase = (P.roundBase + (unsigned long long)w * K + 1ull) << 1;
-            const int flagSlot = (w * K) % SW_FLAG_RING;
-            /* table values of the lane's next attempt are fetched one round ahead (they do not depend on the state) */
-            int xbN = xb[tabBase];
-            real lnuN = us[tabBase], vN = dotRow[0];
+            int fs = (w * K) % SW_FLAG_RING;
+            uint32_t accC = 0, sgnC = 0;
+            uint32_t xbN = ldsU32(pXb);
+            real lnuN, vN;
+            ldsReal(pUs, lnuN);
+            ldsReal(pDot, vN);
+
             for (int rl = 0; rl < Kw; ++rl) {
-#pragma unroll 1
-                for (int ph = 0; ph < 3; ++ph) {
-                    if (ph == 1 && !(mRing & 1)) continue;
-                    if (active && myPhase == ph) {
-                        const int w32 = xbN >> 5, bit = xbN & 31;
-                        const real lnu = lnuN;
-                        real v = vN; /* scaleA (h + 2 sum) against the snapshot */
+                const uint32_t aw = (xbN >> 5) << 2, bit = xbN & 31u;
+                const real lnu = lnuN;
+                real v = vN; /* scaleA (h + 2 sum) against the snapshot, flips of window w-1 included */
+                if (rl + 1 < Kw) { /* next round's table entries (state independent) */
+                    pXb += 4; pUs += (uint32_t)sizeof(real); pDot += (uint32_t)sizeof(real);
+                    xbN = ldsU32(pXb);
+                    ldsReal(pUs, lnuN);
+                    ldsReal(pDot, vN);
+                }
+                {   /* repair with this trotter's own flips earlier in this window */
+                    uint32_t ev = accC;
+                    while (ev) {
+                        const int j = __ffs(ev) - 1;
+                        ev &= ev - 1;
+                        real c;
+                        ldsReal(pCr + (uint32_t)(j * sizeof(real)), c);
+                        v += (((sgnC >> j) & 1u) ? corrScale : -corrScale) * c;
+                    }
+                }
+                pCr += (uint32_t)(2 * K * sizeof(real));
+                const bool conflict = (cmask >> rl) & 1u;
+
+                auto core = [&](int ph) {
+                    if (myPhase == ph) {
                         /* state-dependent shared-memory reads: own word and both neighbours' words */
-                        const uint32_t wv = my32[w32], lv = left32[w32], rv = right32[w32];
-                        const uint32_t cm = remoteMask ? ((lLocal ? 0u : conf[rl]) | (rLocal ? 0u : conf[K + rl])) : 0u;
-                        if (rl + 1 < Kw) { xbN = xb[tabBase + rl + 1]; lnuN = us[tabBase + rl + 1]; vN = dotRow[rl + 1]; }
+                        const uint32_t wv = ldsU32(aMy + aw);
                         const uint32_t up = (wv >> bit) & 1u;
-                        /* repair the snapshot dot product with every flip accepted since the snapshot */
-                        uint32_t ev = accP | ((accC & ((1u << rl) - 1u)) << K);
-                        if (ev) {
-                            const real *cr = cross + ((buf * maxT + lane) * K + rl) * (2 * K);
-                            const uint32_t sg = sgnP | (sgnC << K);
-                            do {
-                                int j = __ffs(ev) - 1;
-                                ev &= ev - 1;
-                                v += (((sg >> j) & 1u) ? corrScale : -corrScale) * cr[j];
-                            } while (ev);
-                        }
+                        real vv = v;
                         if (SQA) {
+                            const uint32_t lv = ldsU32(aLeft + aw), rv = ldsU32(aRight + aw);
                             int nb = (int)((lv >> bit) & 1u) + (int)((rv >> bit) & 1u); /* number of up neighbours */
-                            if (cm) { /* rare: a neighbour owned by another CTA attempted this very spin */
+                            if (conflict) { /* rare: a neighbour owned by another CTA attempted this very spin */
                                 const int x = xs[tabBase + rl];
                                 int ql = ((lv >> bit) & 1u) ? 1 : -1, qr = ((rv >> bit) & 1u) ? 1 : -1;
-                                if (!lLocal && conf[rl]) ql = remoteSpin(0, x, w, rl);
-                                if (!rLocal && conf[K + rl]) qr = remoteSpin(1, x, w, rl);
+                                if (!lLocal && confW[rl]) ql = remoteSpin(0, x, rl);
+                                if (!rLocal && confW[K + rl]) qr = remoteSpin(1, x, rl);
                                 nb = (ql + qr + 2) >> 1;
                             }
-                            v -= P.scaleNb * real(2 * nb - 2);
+                            vv -= nbScale2 * real(nb - 1);
                         }
-                        const bool acc = (up ? v : -v) < lnu; /* exp(-dE beta) > u */
+                        const bool acc = (up ? vv : -vv) < lnu; /* exp(-dE beta) > u */
                         if (acc) {
-                            my32[w32] = wv ^ (1u << bit);
+                            stsU32(aMy + aw, wv ^ (1u << bit));
                             accC |= 1u << rl;
-                            sgnC |= up << rl;
-                            ++nAccepted;
                         }
+                        sgnC |= up << rl;
                         if (publishes) {
                             const unsigned long long fv = flagBase + (unsigned long long)(2 * rl) + (acc ? 1ull : 0ull);
-                            const int fs = (flagSlot + rl) % SW_FLAG_RING;
                             stRelaxed(myFlags + fs, fv);
                             if (mirror0) stRelaxedSys(mirror0 + fs, fv);
                             if (mirror1) stRelaxedSys(mirror1 + fs, fv);
                         }
                     }
                     __syncwarp();
-                }
+                };
+                core(0);
+                if (oddRing) core(1);
+                core(2);
+                if (++fs == SW_FLAG_RING) fs = 0;
             }
-            const long long tLoop = clock64();
-            if (w + 1 < nW) chainHousekeeping(w + 1);
-            const long long tHk = clock64();
-            /* (x, -ln u, h) two windows ahead; reuses the ring slot of window w-1, which nobody reads any more */
-            prepWindow(w + 2, lane, 32);
-            __syncwarp();
-            const long long tPrep = clock64();
-            cycLoop += tLoop - tBusy0; cycHk += tHk - tLoop; cycPrep += tPrep - tHk;
-            accP = accC; sgnP = sgnC; accC = 0; sgnC = 0;
-            busy += clock64() - tBusy0;
+            if (active) accLog[buf * maxT + lane] = accC;
+            nAccepted += (unsigned long long)__popc(accC);
+            accP = accC; sgnP = sgnC;
+            busy += clock64() - t0;
+            barA();
         }
-        __syncthreads();
-        /* new snapshot S_{w+1}; publish the edge trotters for the neighbouring CTAs */
-        for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
-        if (remote && w + 1 < nW) {
-            const int nEdge = (T > 1) ? 2 : 1;
-            for (int i = tid; i < nEdge * NW; i += SW_THREADS) {
-                int e = i / NW, k = i % NW;
-                int t = e ? T - 1 : 0;
-                const unsigned long long v = qcur[(size_t)t * NW + k];
-                const size_t off = (size_t)((w + 1) % SW_SNAP_SLOTS) * NW + k;
-                sBits[(size_t)(y0 + t) * SW_SNAP_SLOTS * NW + off] = v;
-                if (ringSharded) {
-                    if (y0 + t == 0 && P.peerSnapBits[0]) P.peerSnapBits[0][(size_t)(m + 1) * SW_SNAP_SLOTS * NW + off] = v;
-                    if (y0 + t == m - 1 && P.peerSnapBits[1]) P.peerSnapBits[1][(size_t)m * SW_SNAP_SLOTS * NW + off] = v;
-                }
-            }
-            if (ringSharded) __threadfence_system(); else __threadfence();
-        }
-        __syncthreads();
-        if (remote && w + 1 < nW && tid == 0) {
-            const unsigned long long sv = P.snapBase + (unsigned long long)(w + 1);
-            stRelease(sFlags + y0, sv);
-            if (T > 1) stRelease(sFlags + y0 + T - 1, sv);
-            if (ringSharded) {
-                if (y0 == 0 && P.peerSnapFlags[0]) stReleaseSys(P.peerSnapFlags[0] + m + 1, sv);
-                if (y0 + T == m && P.peerSnapFlags[1]) stReleaseSys(P.peerSnapFlags[1] + m, sv);
-            }
+        if (P.stats) {
+            nAccepted = warpSum(nAccepted);
+            if (lane == 0) atomicAdd(P.stats, nAccepted);
         }
     }
 
@@ -567,19 +676,17 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 if (j + e < N) dst[e] = ((nib >> e) & 1u) ? 1 : -1;
         }
     }
-    if (chainWarp && P.stats) {
-        nAccepted = warpSum(nAccepted);
+    if (P.stats) {
         nWaits = warpSum(nWaits);
         if (lane == 0) {
-            atomicAdd(P.stats, nAccepted);
-            atomicAdd(P.stats + 1, nWaits);
-            atomicAdd(P.stats + 3, (unsigned long long)busy); /* chain warp: cycles spent replaying windows */
-            atomicAdd(P.stats + 4, (unsigned long long)cycLoop);
-            atomicAdd(P.stats + 5, (unsigned long long)cycHk);
-            atomicAdd(P.stats + 6, (unsigned long long)cycPrep);
+            if (nWaits) atomicAdd(P.stats + 1, nWaits);
+            if (dotWarp && dw == 0) atomicAdd(P.stats + 2, (unsigned long long)busy); /* dot warp 0: cycles spent on dot products */
+            if (chainWarp) atomicAdd(P.stats + 3, (unsigned long long)busy);          /* chain warp: cycles spent replaying */
+            if (helperWarp) atomicAdd(P.stats + 5, (unsigned long long)busy);         /* helper warp: snapshots, publication, masks */
+            if (prepWarp) atomicAdd(P.stats + 6, (unsigned long long)busy);           /* prep warp: Philox tables */
         }
     }
-    if (warp == 0 && lane == 0 && P.stats) atomicAdd(P.stats + 2, (unsigned long long)busy); /* dot warp 0: cycles spent on dot products */
+    (void)cycA; (void)cycB;
 }
 
 /* ---------------- small element-wise kernels ---------------- */
@@ -796,7 +903,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     const int maxT = (m_ + G - 1) / G;
     const int nw64 = packedWords64(N_);
     int chunkElems = std::min((int)ldJ_, (int)(4096 / sizeof(real)));
-    int stages = 3;
+    int stages = 4;
     int K = SW_MAX_K; /* look-ahead window; shrinks when many trotters share a CTA (tables grow with T K^2) */
     for (;;) {
         SweepSmem<real> L(maxT, nw64, chunkElems, stages, K);
@@ -1116,6 +1223,14 @@ template <class real> void B200DenseGraphAnnealer<real>::getStats(unsigned long 
     *waits = h[1];
     lastBarrierWaitDot_ = h[2];
     lastBarrierWaitChain_ = h[3];
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::getCounters(unsigned long long out[8]) const {
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (dStats_.p) {
+        dev_->d2h(out, dStats_.p, 8 * sizeof(unsigned long long));
+        dev_->synchronize();
+    }
 }
 
 template class B200DenseGraphAnnealer<float>;

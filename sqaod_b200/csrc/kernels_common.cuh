@@ -66,6 +66,20 @@ __device__ __forceinline__ uint64_t l2PolicyEvictLast() {
     return p;
 }
 
+/* ---- explicit 32-bit shared-memory accesses (the accept chain keeps its table addresses in registers) ---- */
+__device__ __forceinline__ uint32_t ldsU32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stsU32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void ldsReal(uint32_t a, float &v) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); }
+__device__ __forceinline__ void ldsReal(uint32_t a, double &v) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); }
+__device__ __forceinline__ void stsReal(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void stsReal(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+/* named barrier over `count` threads (a multiple of 32) of the CTA; warps may arrive from different code paths */
+__device__ __forceinline__ void namedBarSync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 /* ---- gpu-scope release/acquire on 64-bit flags in global memory (inter-CTA hand-off) ---- */
 __device__ __forceinline__ void stRelease(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

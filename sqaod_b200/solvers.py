@@ -195,7 +195,10 @@ class DenseGraphAnnealer(_SolverBase):
         _lib.check(L.sqb_dg_annealer_get_stats(self._cobj, C.byref(a), C.byref(w), self._dt))
         d = C.c_ulonglong(0); c = C.c_ulonglong(0)
         _lib.check(L.sqb_dg_annealer_get_barrier_cycles(self._cobj, C.byref(d), C.byref(c), self._dt))
-        return {'accepted': a.value, 'flag_waits': w.value, 'barrier_cycles_dot': d.value, 'barrier_cycles_chain': c.value}
+        raw = (C.c_ulonglong * 8)()
+        _lib.check(L.sqb_dg_annealer_get_counters(self._cobj, raw, self._dt))
+        return {'accepted': a.value, 'flag_waits': w.value, 'barrier_cycles_dot': d.value, 'barrier_cycles_chain': c.value,
+                'helper_cycles': raw[5], 'prep_cycles': raw[6]}
 
 
 def dense_graph_annealer(W=None, optimize=minimize, dtype=np.float64, device=None, **prefs):

@@ -24,8 +24,8 @@ for N, m in sizes:
     ann._device.synchronize(); dt = (time.perf_counter() - t) / n * 1e3
     s1 = ann.get_stats(); G = min(148, m)
     d = {k: (s1[k] - s0[k]) / G / CLK / n for k in s1 if 'cycles' in k}
-    print('N=%d m=%d: %.3f ms/step | per CTA busy ms: dot warp %.3f chain warp %.3f helper warp %.3f prep warp %.3f | '
+    print('N=%d m=%d: %.3f ms/step | per CTA busy ms: dot warp %.3f chain warp %.3f helper warp %.3f prep warp %.3f | chain waits: rows %.3f nb %.3f | '
           'flag polls/step %.0f accepted/step %.0f' %
-          (N, m, dt, d['barrier_cycles_dot'], d['barrier_cycles_chain'], d['helper_cycles'], d['prep_cycles'],
+          (N, m, dt, d['barrier_cycles_dot'], d['barrier_cycles_chain'], d['helper_cycles'], d['prep_cycles'], d['chain_wait_rows_cycles'], d['chain_wait_neighbour_cycles'],
            (s1['flag_waits'] - s0['flag_waits']) / n,
            (s1['accepted'] - s0['accepted']) / n))

@@ -86,7 +86,7 @@ int sqb_dg_annealer_get_spins(sqb_handle ann, signed char *q, int dtype);
 int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, unsigned long long *chain, int dtype);
 /* raw sweep counters summed over CTAs since prepare(): [0] accepted flips, [1] flag polls, [2] dot-warp-0 busy cycles,
  * [3] chain-warp busy cycles, [5] helper-warp busy cycles (snapshots, conflict masks), [6] prep-warp busy cycles (Philox
- * tables), [4] and [7] unused */
+ * tables), [4] / [7] chain-warp cycles waiting for dot products / for neighbour data */
 int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int dtype);
 
 /* replica batch (no reference counterpart): R independent replicas of the problem, replica r seeded

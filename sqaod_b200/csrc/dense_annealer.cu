@@ -38,8 +38,8 @@
 
 namespace sqb {
 
-enum { SW_MAX_K = 16, SW_DOT_WARPS = 12, SW_THREADS = 512, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4,
-       SW_CHAIN_WARP = 0, SW_HELPER_WARP = 4, SW_PREP_WARP = 8 /* warp 12 is a spare; the dot warps are those with warp & 3 != 0 */ };
+enum { SW_MAX_K = 16, SW_DOT_WARPS = 12, SW_THREADS = 512, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4, SW_TAB_SLOTS = 4,
+       SW_CHAIN_WARP = 0, SW_SNAP_WARP = 4, SW_PREP_WARP = 8, SW_NB_WARP = 12 /* the dot warps are those with warp & 3 != 0 */ };
 
 template <class real> struct SweepParams {
     const real *J;
@@ -76,22 +76,22 @@ template <class real> struct SweepSmem {
         ring = o; o += (size_t)SW_DOT_WARPS * stages * chunkElems * sizeof(real);
         bars = o; o += (size_t)SW_DOT_WARPS * stages * 8;
         qcur = o; o += (size_t)T * nw64 * 8;
-        qsnap = o; o += (size_t)T * nw64 * 8;
+        qsnap = o; o += (size_t)2 * T * nw64 * 8;
         nbsnap = o; o += (size_t)2 * 2 * nw64 * 8;
         dots = o; o += (size_t)2 * T * K * sizeof(real);
         o = (o + 15) & ~(size_t)15;
         cross = o; o += (size_t)2 * T * K * (2 * K) * sizeof(real);
-        xs = o; o += (size_t)3 * T * K * 4;
-        xb = o; o += (size_t)3 * T * K * 4;
+        xs = o; o += (size_t)SW_TAB_SLOTS * T * K * 4;
+        xb = o; o += (size_t)SW_TAB_SLOTS * T * K * 4;
         o = (o + 15) & ~(size_t)15;
-        us = o; o += (size_t)3 * T * K * sizeof(real);
-        hs = o; o += (size_t)3 * T * K * sizeof(real);
-        xn = o; o += (size_t)2 * 3 * K * 4;
+        us = o; o += (size_t)SW_TAB_SLOTS * T * K * sizeof(real);
+        hs = o; o += (size_t)SW_TAB_SLOTS * T * K * sizeof(real);
+        xn = o; o += (size_t)2 * SW_TAB_SLOTS * K * 4;
         conf = o; o += (size_t)2 * 2 * K * 4;
         confAny = o; o += 16;
         accLog = o; o += (size_t)2 * T * 4;
         o = (o + 15) & ~(size_t)15;
-        counter = o; o += 16;
+        counter = o; o += 32;
         total = (o + 127) & ~(size_t)127;
     }
 };
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
      * accept chain and its helpers, the twelve streaming dot warps share the other three. */
     const bool dotWarp = (warp & 3) != 0;
     const int dw = (warp >> 2) * 3 + (warp & 3) - 1; /* dot warp index 0..11 */
-    const bool chainWarp = (warp == SW_CHAIN_WARP), helperWarp = (warp == SW_HELPER_WARP), prepWarp = (warp == SW_PREP_WARP);
+    const bool chainWarp = (warp == SW_CHAIN_WARP), snapWarp = (warp == SW_SNAP_WARP), prepWarp = (warp == SW_PREP_WARP), nbWarp = (warp == SW_NB_WARP);
     const int N = P.N, m = P.m;
     const int G = gridDim.x, cta = blockIdx.x;
     const int baseT = m / G, remT = m % G;
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     /* (x, -ln u, h[x]) of every attempt of window w for the owned trotters, plus the remote neighbours' x */
     auto prepWindow = [&](int w, int t0, int nthr) {
         if (w >= nW) return;
-        const int Kw = roundsIn(w), slot = w % 3;
+        const int Kw = roundsIn(w), slot = w & (SW_TAB_SLOTS - 1);
         for (int idx = t0; idx < Kw * T; idx += nthr) {
             int t = idx % T, rl = idx / T;
             Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)gOf(y0 + t));
@@ -225,46 +225,54 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             for (int idx = t0; idx < 2 * Kw; idx += nthr) {
                 int side = idx / Kw, rl = idx % Kw;
                 Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)(side ? yRight : yLeft));
-                xn[(side * 3 + slot) * K + rl] = (int)(p.w[0] % (uint32_t)N);
+                xn[(side * SW_TAB_SLOTS + slot) * K + rl] = (int)(p.w[0] % (uint32_t)N);
             }
         }
     };
 
     unsigned long long nWaits = 0;
+    long long waited = 0; /* cycles lane 0 of this warp spent waiting for another warp or CTA */
 
     /* helper warp: what chain window wn needs from the neighbouring CTAs -- their snapshot S_{wn-1} and, per attempt of
      * my edge trotters, the mask of neighbour attempts (previous + current window) that hit the same spin index.
      * Written to buffer wn & 1 while the chain replays window wn - 1 out of the other buffer. */
     auto neighbourWindow = [&](int wn) {
         if (!remote) return;
-        const int Kn = roundsIn(wn), slotN = wn % 3, bN = wn & 1;
+        const int Kn = roundsIn(wn), slotN = wn & (SW_TAB_SLOTS - 1), bN = wn & 1;
         if (wn >= 2) {
-            for (int side = 0; side < 2; ++side) {
+            if (lane < 2) { /* lane 0 / 1 wait for the left / right neighbour's S_{wn-1} */
+                const int sl = lane ? slotR : slotL;
+                const unsigned long long want = P.snapBase + (unsigned long long)(wn - 1);
+                const long long t0 = clock64();
+                if (ringSharded) { while (ldAcquireSys(sFlags + sl) < want) { ++nWaits; __nanosleep(20); } }
+                else { while (ldAcquire(sFlags + sl) < want) { ++nWaits; __nanosleep(20); } }
+                if (lane == 0) waited += clock64() - t0;
+            }
+            __syncwarp();
+            for (int i = lane; i < 2 * NW; i += 32) {
+                const int side = i / NW, k = i - side * NW;
                 const int sl = side ? slotR : slotL;
-                if (lane == 0) {
-                    const unsigned long long want = P.snapBase + (unsigned long long)(wn - 1);
-                    if (ringSharded) { while (ldAcquireSys(sFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
-                    else { while (ldAcquire(sFlags + sl) < want) { ++nWaits; __nanosleep(50); } }
-                }
-                __syncwarp();
-                const unsigned long long *src = sBits + ((size_t)sl * SW_SNAP_SLOTS + ((wn - 1) % SW_SNAP_SLOTS)) * NW;
-                unsigned long long *dst = nbsnap + (size_t)(bN * 2 + side) * NW;
-                for (int i = lane; i < NW; i += 32) dst[i] = __ldcg(src + i);
+                nbsnap[(size_t)(bN * 2 + side) * NW + k] = __ldcg(sBits + ((size_t)sl * SW_SNAP_SLOTS + ((wn - 1) % SW_SNAP_SLOTS)) * NW + k);
             }
         }
-        for (int side = 0; side < 2; ++side) {
-            int nbx = -1;
-            if (lane < K) { if (wn > 0) nbx = xn[(side * 3 + (wn - 1) % 3) * K + lane]; }
-            else if (lane < 2 * K && lane - K < Kn) nbx = xn[(side * 3 + slotN) * K + (lane - K)];
-            const int tEdge = side ? T - 1 : 0;
-            uint32_t any = 0;
-            for (int rl = 0; rl < Kn; ++rl) {
-                int xe = xs[(slotN * maxT + tEdge) * K + rl];
-                uint32_t hit = __ballot_sync(0xffffffffu, nbx == xe);
-                if (lane == 0) conf[(bN * 2 + side) * K + rl] = hit;
-                any |= (hit ? 1u : 0u) << rl;
+        {   /* lane -> (side, round of my edge trotter): which of the neighbour's 2K attempts (previous + this window) drew
+             * the same spin index */
+            const int side = lane / K, rl = lane % K;
+            uint32_t mask = 0;
+            if (side < 2 && rl < Kn) {
+                const int xe = xs[(slotN * maxT + (side ? T - 1 : 0)) * K + rl];
+                const int *xp = xn + (side * SW_TAB_SLOTS + ((wn - 1) & (SW_TAB_SLOTS - 1))) * K;
+                const int *xc = xn + (side * SW_TAB_SLOTS + slotN) * K;
+                if (wn > 0) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) mask |= (xp[j] == xe ? 1u : 0u) << j;
+                }
+#pragma unroll
+                for (int j = 0; j < K; ++j) mask |= ((j < Kn && xc[j] == xe) ? 1u : 0u) << (K + j);
+                conf[(bN * 2 + side) * K + rl] = mask;
             }
-            if (lane == 0) confAny[bN * 2 + side] = any;
+            const uint32_t nz = __ballot_sync(0xffffffffu, mask != 0u);
+            if (lane < 2) confAny[bN * 2 + lane] = (nz >> (lane * K)) & ((1u << K) - 1u);
         }
         __syncwarp();
     };
@@ -310,15 +318,41 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     }
     prepWindow(0, tid, SW_THREADS);
     prepWindow(1, tid, SW_THREADS);
+    prepWindow(2, tid, SW_THREADS);
     __syncthreads();
     for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
     for (int i = tid; i < 2 * NW; i += SW_THREADS) nbsnap[2 * NW + i] = nbsnap[i]; /* windows 0 and 1 both start from S_0 */
-    if (helperWarp) neighbourWindow(0);
+    if (nbWarp) neighbourWindow(0);
+
+    /* ---------------- hand-off counters between the warps of this CTA (shared memory, release/acquire at CTA scope) ------
+     * There is no CTA-wide barrier inside the sweep: every warp runs its own loop over the windows and waits only for what it
+     * consumes.
+     *   rowsDone[b]  rows of the windows of parity b whose dot product + cross terms are stored      (dot warps -> chain)
+     *   replayDone   windows replayed                                                                  (chain -> helper)
+     *   snapCount    snapshots S_0 .. S_{c-1} built; S_k = spins before window k, kept in qsnap[k & 1]  (helper -> dot, prep)
+     *   nbCount      windows whose neighbour snapshot + conflict masks are in place                     (helper -> chain)
+     *   prepCount    windows whose (x, -ln u, h) tables are in place (4 slots)                          (prep -> dot, helper)
+     * Rows of window w are reduced against S_{w-1} (S_0 for w = 0), i.e. they can start as soon as window w-2 has been
+     * replayed, one full window before the chain needs them. */
+    const uint32_t aSync = smemAddr(taskCounter);
+    const uint32_t aRowsDone = aSync + 4, aReplayDone = aSync + 12, aSnapCount = aSync + 16, aNbCount = aSync + 20, aPrepCount = aSync + 24;
+    auto waitCount = [&](uint32_t addr, uint32_t want, unsigned ns) { /* whole warp; lane 0 polls */
+        if (lane == 0 && ldAcquireCta(addr) < want) {
+            const long long t0 = clock64();
+            while (ldAcquireCta(addr) < want) { if (ns) __nanosleep(ns); }
+            waited += clock64() - t0;
+        }
+        __syncwarp();
+    };
+    auto signalCount = [&](uint32_t addr, uint32_t v) { /* whole warp: everything the warp wrote is visible before the count */
+        __syncwarp();
+        if (lane == 0) stReleaseCta(addr, v);
+    };
 
     /* ---------------- dot warps: per-warp TMA ring state ---------------- */
     /* task g = w * (K*T) + id, id = rl * T + t.  Tasks are CLAIMED dynamically (shared counter) by whichever dot warp is about to
      * issue a new row, so a warp slowed down by HBM/L2 queueing simply takes fewer rows.  Claims are monotone, hence in
-     * window order; a warp prefetches at most its next row across a window boundary and consumes it after the barrier. */
+     * window order; the TMA ring keeps streaming across window boundaries (rows are known from Philox alone). */
     const int TPW = K * T;                                   /* tasks per full window */
     const int totalTasks = (nW - 1) * TPW + roundsIn(nW - 1) * T;
     int ic = 0, ix = 0;                     /* issue cursor (lane 0): chunk within the row being issued, its row index */
@@ -339,8 +373,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             if (fifo0 < 0) fifo0 = g; else fifo1 = g;
             const int iw = g / TPW, iid = g - iw * TPW;
             const int t = iid % T, rl = iid / T;
-            Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(iw * K + rl), (uint32_t)gOf(y0 + t));
-            ix = (int)(p.w[0] % (uint32_t)N);
+            if (ldAcquireCta(aPrepCount) > (uint32_t)iw) { /* the window's tables are already in place */
+                ix = xs[((iw & (SW_TAB_SLOTS - 1)) * maxT + t) * K + rl];
+            } else {
+                Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(iw * K + rl), (uint32_t)gOf(y0 + t));
+                ix = (int)(p.w[0] % (uint32_t)N);
+            }
         }
         const int elems = min(CH, P.ldJ - ic * CH);
         const uint32_t bytes = (uint32_t)(elems * sizeof(real));
@@ -349,111 +387,106 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         if (++iStage == S) iStage = 0;
         if (++ic == CPR) ic = 0;
     };
-    if (dotWarp && lane == 0)
-        for (int s = 0; s < S; ++s) issueNext();
 
-    /* consume every task this warp owns in window w; results go to buffer w & 1 */
-    auto dotWindow = [&](int w) {
-        const int buf = w & 1;
-        for (;;) {
-            const int g = __shfl_sync(0xffffffffu, fifo0, 0); /* oldest row this warp has claimed and not yet reduced */
-            if (g < 0 || g / TPW != w) break;                 /* nothing left, or it belongs to a later window */
-            const int id = g - w * TPW;
-            const int t = id % T, rl = id / T;
-            /* column whose J[x][col] this lane must pick up: lane j < K -> round j of window w-1, else round j-K of w */
-            int px = -1;
-            if (lane < K) { if (w > 0) px = xs[(((w - 1) % 3) * maxT + t) * K + lane]; }
-            else if (lane < 2 * K && lane - K < rl) px = xs[((w % 3) * maxT + t) * K + (lane - K)];
-            real crossv = real(0);
-            real a0 = real(0), a1 = real(0), a2 = real(0), a3 = real(0);
-            const unsigned long long *qrow = qsnap + (size_t)t * NW;
-            for (int c = 0; c < CPR; ++c) {
-                mbarWait(&myBars[cStage], cParity);
-                const real *buf_ = myRing + (size_t)cStage * CH;
-                const int c0 = c * CH;
-                const int groups = min(GPC, (P.ldJ - c0) >> 7);
-                const int g0 = c * GPC;
-                unsigned long long bits = qrow[((g0 >> 4) << 5) + lane] >> ((g0 & 15) << 2);
-                const real *src = buf_ + lane * 4;
-                if (groups == 16) {
-                    const uint32_t blo = (uint32_t)bits, bhi = (uint32_t)(bits >> 32);
+    /* reduce the row of task g (window w) against the snapshot the window is defined on; results go to buffer w & 1 */
+    auto dotRow = [&](int g, int w) {
+        const int buf = w & 1, slot = w & (SW_TAB_SLOTS - 1);
+        const int id = g - w * TPW;
+        const int t = id % T, rl = id / T;
+        /* column whose J[x][col] this lane must pick up: lane j < K -> round j of window w-1, else round j-K of w */
+        int px = -1;
+        if (lane < K) { if (w > 0) px = xs[(((w - 1) & (SW_TAB_SLOTS - 1)) * maxT + t) * K + lane]; }
+        else if (lane < 2 * K && lane - K < rl) px = xs[(slot * maxT + t) * K + (lane - K)];
+        real crossv = real(0);
+        real a0 = real(0), a1 = real(0), a2 = real(0), a3 = real(0);
+        const unsigned long long *qrow = qsnap + ((size_t)((w > 0) ? ((w - 1) & 1) : 0) * maxT + t) * NW;
+        for (int c = 0; c < CPR; ++c) {
+            mbarWait(&myBars[cStage], cParity);
+            const real *buf_ = myRing + (size_t)cStage * CH;
+            const int c0 = c * CH;
+            const int groups = min(GPC, (P.ldJ - c0) >> 7);
+            const int g0 = c * GPC;
+            unsigned long long bits = qrow[((g0 >> 4) << 5) + lane] >> ((g0 & 15) << 2);
+            const real *src = buf_ + lane * 4;
+            if (groups == 16) {
+                const uint32_t blo = (uint32_t)bits, bhi = (uint32_t)(bits >> 32);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) accumGroup(src + i * 128, (blo >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+                for (int i = 0; i < 8; ++i) accumGroup(src + i * 128, (blo >> (4 * i)) & 0xfu, a0, a1, a2, a3);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) accumGroup(src + (i + 8) * 128, (bhi >> (4 * i)) & 0xfu, a0, a1, a2, a3);
-                } else if (groups == 8) {
-                    const uint32_t blo = (uint32_t)bits;
+                for (int i = 0; i < 8; ++i) accumGroup(src + (i + 8) * 128, (bhi >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+            } else if (groups == 8) {
+                const uint32_t blo = (uint32_t)bits;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) accumGroup(src + i * 128, (blo >> (4 * i)) & 0xfu, a0, a1, a2, a3);
-                } else {
-                    for (int i = 0; i < groups; ++i) accumGroup(src + i * 128, (uint32_t)(bits >> (4 * i)) & 0xfu, a0, a1, a2, a3);
-                }
-                if (px >= c0 && px < c0 + (groups << 7)) crossv = buf_[px - c0];
-                __syncwarp();
-                if (lane == 0) {
-                    if (c == CPR - 1) { fifo0 = fifo1; fifo1 = -1; } /* this row is done: make room before claiming */
-                    issueNext();
-                }
-                if (++cStage == S) { cStage = 0; cParity ^= 1u; }
+                for (int i = 0; i < 8; ++i) accumGroup(src + i * 128, (blo >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+            } else {
+                for (int i = 0; i < groups; ++i) accumGroup(src + i * 128, (uint32_t)(bits >> (4 * i)) & 0xfu, a0, a1, a2, a3);
             }
-            real s = warpSum((a0 + a1) + (a2 + a3));
-            if (lane == 0) dots[(buf * maxT + t) * K + rl] = P.scaleA * (hs[((w % 3) * maxT + t) * K + rl] + real(2) * s);
-            if (lane < 2 * K) cross[((buf * maxT + t) * K + rl) * (2 * K) + lane] = crossv;
+            if (px >= c0 && px < c0 + (groups << 7)) crossv = buf_[px - c0];
+            __syncwarp();
+            if (lane == 0) {
+                if (c == CPR - 1) { fifo0 = fifo1; fifo1 = -1; } /* this row is done: make room before claiming */
+                issueNext();
+            }
+            if (++cStage == S) { cStage = 0; cParity ^= 1u; }
         }
+        real s = warpSum((a0 + a1) + (a2 + a3));
+        if (lane == 0) dots[(buf * maxT + t) * K + rl] = P.scaleA * (hs[(slot * maxT + t) * K + rl] + real(2) * s);
+        if (lane < 2 * K) cross[((buf * maxT + t) * K + rl) * (2 * K) + lane] = crossv;
+        __syncwarp();
+        if (lane == 0) redAddReleaseCta(aRowsDone + 4u * (uint32_t)buf, 1u);
     };
 
-    /* prologue: dot products of window 0 (against the launch state) */
+    if (tid == 0) {
+        stReleaseCta(aRowsDone, 0u); stReleaseCta(aRowsDone + 4, 0u); stReleaseCta(aReplayDone, 0u);
+        stReleaseCta(aSnapCount, 1u); stReleaseCta(aNbCount, 1u); stReleaseCta(aPrepCount, 3u);
+    }
     __syncthreads();
-    if (dotWarp) dotWindow(0);
-    __syncthreads();
-
-    /* Window protocol (w = 0 .. nW-1), all hand-offs inside the CTA through two barriers:
-     *   chain  : fold window w-1's flips into dots[w], replay window w on qcur, log its accept bits            | A
-     *   helper : apply window w-1's flips to qsnap (= S_w)   | B | publish S_w, fetch neighbours' S_w, masks   | A
-     *   prep   :                                              | B | (x, -ln u, h) of window w+2                  | A
-     *   dot    :                                              | B | dot products of window w+1 against S_w      | A
-     * so the chain never waits for a copy or a publication, only for the dot products of its next window. */
-    auto barA = [&]() { namedBarSync(1, SW_THREADS); };
-    auto barB = [&]() { namedBarSync(2, SW_THREADS - 64); }; /* everyone but the chain warp and the spare warp */
-    long long busy = 0, cycA = 0, cycB = 0;
-    auto touchSmem = [&]() { /* BAR.SYNC blocks lazily: touch shared memory so that waiting is not booked as work */
-        unsigned int dummy;
-        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(dummy) : "r"(smemAddr(taskCounter)) : "memory");
-    };
+    const long long tLoop0 = clock64();
 
     if (dotWarp) {
-        for (int w = 0; w < nW; ++w) {
-            barB();
-            touchSmem();
-            const long long t0 = clock64();
-            if (w + 1 < nW) dotWindow(w + 1);
-            busy += clock64() - t0;
-            barA();
+        if (lane == 0)
+            for (int s = 0; s < S; ++s) issueNext();
+        int curW = -1;
+        for (;;) {
+            const int g = __shfl_sync(0xffffffffu, fifo0, 0); /* oldest row this warp has claimed and not yet reduced */
+            if (g < 0) break;
+            const int w = g / TPW;
+            if (w != curW) { /* first row of a later window: its snapshot S_{w-1} and its tables must be in place */
+                waitCount(aSnapCount, (uint32_t)w, 20);
+                waitCount(aPrepCount, (uint32_t)w + 1u, 20);
+                curW = w;
+            }
+            dotRow(g, w);
         }
-    } else if (helperWarp) {
-        uint32_t *qsnap32 = reinterpret_cast<uint32_t *>(qsnap);
-        for (int w = 0; w < nW; ++w) {
-            touchSmem();
-            const long long t0 = clock64();
-            if (w > 0 && lane < T) { /* S_w = S_{w-1} with the accepted flips of window w-1 */
-                uint32_t bitsAcc = accLog[((w - 1) & 1) * maxT + lane];
-                const int *xbRow = xb + (((w - 1) % 3) * maxT + lane) * K;
-                uint32_t *row = qsnap32 + (size_t)lane * 2 * NW;
-                while (bitsAcc) {
-                    const int rl = __ffs(bitsAcc) - 1;
-                    bitsAcc &= bitsAcc - 1;
-                    const int xbv = xbRow[rl];
-                    row[xbv >> 5] ^= 1u << (xbv & 31);
+    } else if (snapWarp) {
+        /* S_w for the dot warps and for the neighbouring CTAs, as soon as window w-1 has been replayed */
+        for (int w = 1; w < nW; ++w) {
+            waitCount(aReplayDone, (uint32_t)w, 20);
+            {   /* S_w = S_{w-1} with the accepted flips of window w-1 */
+                const unsigned long long *src = qsnap + (size_t)((w - 1) & 1) * maxT * NW;
+                unsigned long long *dst = qsnap + (size_t)(w & 1) * maxT * NW;
+                for (int i = lane; i < T * NW; i += 32) dst[i] = src[i];
+                __syncwarp();
+                if (lane < T) {
+                    uint32_t bitsAcc = accLog[((w - 1) & 1) * maxT + lane];
+                    const int *xbRow = xb + (((w - 1) & (SW_TAB_SLOTS - 1)) * maxT + lane) * K;
+                    uint32_t *row = reinterpret_cast<uint32_t *>(dst + (size_t)lane * NW);
+                    while (bitsAcc) {
+                        const int rl = __ffs(bitsAcc) - 1;
+                        bitsAcc &= bitsAcc - 1;
+                        const int xbv = xbRow[rl];
+                        row[xbv >> 5] ^= 1u << (xbv & 31);
+                    }
                 }
             }
-            __syncwarp();
-            barB();
-            if (remote && w >= 1) { /* publish the edge trotters' S_w for the neighbouring CTAs */
+            signalCount(aSnapCount, (uint32_t)w + 1u);
+            if (remote) { /* publish the edge trotters' S_w for the neighbouring CTAs */
+                const unsigned long long *snapW = qsnap + (size_t)(w & 1) * maxT * NW;
                 const int nEdge = (T > 1) ? 2 : 1;
                 for (int i = lane; i < nEdge * NW; i += 32) {
-                    int e = i / NW, k = i % NW;
-                    int t = e ? T - 1 : 0;
-                    const unsigned long long v = qsnap[(size_t)t * NW + k];
+                    const int e = i / NW, k = i - e * NW;
+                    const int t = e ? T - 1 : 0;
+                    const unsigned long long v = snapW[(size_t)t * NW + k];
                     const size_t off = (size_t)(w % SW_SNAP_SLOTS) * NW + k;
                     sBits[(size_t)(y0 + t) * SW_SNAP_SLOTS * NW + off] = v;
                     if (ringSharded) {
@@ -461,7 +494,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                         if (y0 + t == m - 1 && P.peerSnapBits[1]) P.peerSnapBits[1][(size_t)m * SW_SNAP_SLOTS * NW + off] = v;
                     }
                 }
-                if (ringSharded) __threadfence_system(); else __threadfence();
+                /* the warp barrier orders every lane's stores before lane 0's release (cumulative), so no per-lane
+                 * fence is needed inside the GPU; across GPUs keep the explicit system fence */
+                if (ringSharded) __threadfence_system();
                 __syncwarp();
                 if (lane == 0) {
                     const unsigned long long sv = P.snapBase + (unsigned long long)w;
@@ -473,22 +508,23 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                     }
                 }
             }
-            if (w + 1 < nW) neighbourWindow(w + 1);
-            busy += clock64() - t0;
-            barA();
+        }
+    } else if (nbWarp) {
+        /* the neighbours' S_{wn-1} and the conflict masks of window wn, into the buffers window wn-2 has finished with */
+        for (int wn = 1; wn < nW; ++wn) {
+            waitCount(aReplayDone, (uint32_t)(wn - 1), 20);
+            waitCount(aPrepCount, (uint32_t)wn + 1u, 20);
+            neighbourWindow(wn);
+            signalCount(aNbCount, (uint32_t)wn + 1u);
         }
     } else if (prepWarp) {
-        for (int w = 0; w < nW; ++w) {
-            barB();
-            touchSmem();
-            const long long t0 = clock64();
-            prepWindow(w + 2, lane, 32); /* reuses the table slot of window w-1, which the helper has just finished with */
-            busy += clock64() - t0;
-            barA();
+        /* tables of window wp go to the slot of window wp-4, dead once S_{wp-2} is built (window wp-3 replayed) */
+        for (int wp = 3; wp < nW; ++wp) {
+            waitCount(aSnapCount, (uint32_t)wp - 1u, 20);
+            prepWindow(wp, lane, 32);
+            signalCount(aPrepCount, (uint32_t)wp + 1u);
         }
-    } else if (!chainWarp) {
-        for (int w = 0; w < nW; ++w) barA(); /* spare warp: keeps the accept chain's scheduler free */
-    } else {
+    } else if (chainWarp) {
         /* ---------------- the accept chain: lane = trotter ---------------- */
         const bool active = (lane < T);
         const int tl = active ? lane : 0;
@@ -512,13 +548,17 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         const real nbScale2 = real(2) * P.scaleNb;
         uint32_t accP = 0, sgnP = 0;
         unsigned long long nAccepted = 0;
+        long long waitedNb = 0;
 
         for (int w = 0; w < nW; ++w) {
-            touchSmem();
-            const long long t0 = clock64();
-            const int Kw = roundsIn(w), buf = w & 1, slot = w % 3;
+            const int Kw = roundsIn(w), buf = w & 1, slot = w & (SW_TAB_SLOTS - 1);
             const unsigned long long *nbRows = nbsnap + (size_t)buf * 2 * NW;
             const uint32_t *confW = conf + buf * 2 * K;
+            /* every row of this window reduced (and, through it, the window's tables in place); neighbour data in place */
+            waitCount(aRowsDone + 4u * (uint32_t)buf, (uint32_t)((w >> 1) * TPW + Kw * T), 0);
+            const long long waitedRows = waited;
+            if (remote) waitCount(aNbCount, (uint32_t)w + 1u, 0);
+            waitedNb += waited - waitedRows;
 
             /* spin of a trotter owned by another CTA: published snapshot, corrected by the accept bits of the neighbour's
              * attempts that hit the same spin index since the snapshot */
@@ -545,8 +585,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 return v;
             };
 
-            /* 1. fold the flips of window w-1 (known since the last barrier) into the snapshot dot products of window w:
-             *    one (trotter, round) item per lane, so this is off the serial path */
+            /* 1. fold the flips of window w-1 into the snapshot dot products of window w: one (trotter, round) item per
+             *    lane, so this is off the serial path */
             if (__any_sync(0xffffffffu, accP != 0u)) {
                 for (int i0 = 0; i0 < T * K; i0 += 32) {
                     const int i = i0 + lane;
@@ -653,14 +693,19 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             if (active) accLog[buf * maxT + lane] = accC;
             nAccepted += (unsigned long long)__popc(accC);
             accP = accC; sgnP = sgnC;
-            busy += clock64() - t0;
-            barA();
+            signalCount(aReplayDone, (uint32_t)w + 1u);
         }
         if (P.stats) {
             nAccepted = warpSum(nAccepted);
-            if (lane == 0) atomicAdd(P.stats, nAccepted);
+            if (lane == 0) {
+                atomicAdd(P.stats, nAccepted);
+                atomicAdd(P.stats + 4, (unsigned long long)(waited - waitedNb)); /* chain: cycles waiting for dot products */
+                atomicAdd(P.stats + 7, (unsigned long long)waitedNb);            /* chain: cycles waiting for neighbour data */
+            }
         }
     }
+    const long long busy = (clock64() - tLoop0) - waited; /* cycles lane 0 of this warp spent working */
+    __syncthreads();
 
     /* ---------------- write the spins back ---------------- */
     {
@@ -682,11 +727,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             if (nWaits) atomicAdd(P.stats + 1, nWaits);
             if (dotWarp && dw == 0) atomicAdd(P.stats + 2, (unsigned long long)busy); /* dot warp 0: cycles spent on dot products */
             if (chainWarp) atomicAdd(P.stats + 3, (unsigned long long)busy);          /* chain warp: cycles spent replaying */
-            if (helperWarp) atomicAdd(P.stats + 5, (unsigned long long)busy);         /* helper warp: snapshots, publication, masks */
+            if (snapWarp || nbWarp) atomicAdd(P.stats + 5, (unsigned long long)busy); /* snapshot + neighbour warps */
             if (prepWarp) atomicAdd(P.stats + 6, (unsigned long long)busy);           /* prep warp: Philox tables */
         }
     }
-    (void)cycA; (void)cycB;
 }
 
 /* ---------------- small element-wise kernels ---------------- */
@@ -902,18 +946,28 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     replicasPerLaunch_ = std::max(1, std::min(nReplicas_, dev_->numSMs() / G));
     const int maxT = (m_ + G - 1) / G;
     const int nw64 = packedWords64(N_);
-    int chunkElems = std::min((int)ldJ_, (int)(4096 / sizeof(real)));
-    int stages = 4;
-    int K = SW_MAX_K; /* look-ahead window; shrinks when many trotters share a CTA (tables grow with T K^2) */
-    for (;;) {
-        SweepSmem<real> L(maxT, nw64, chunkElems, stages, K);
-        if (L.total <= dev_->smemPerBlockOptin()) break;
-        if (K > 4 && (size_t)2 * maxT * K * 2 * K * sizeof(real) > (size_t)48 * 1024) K >>= 1;
-        else if (stages > 2) --stages;
-        else if (chunkElems > 512) chunkElems >>= 1;
-        else if (K > 4) K >>= 1;
-        else if (chunkElems > 128) chunkElems >>= 1;
-        else sqb_throwError("problem too large for the sweep kernel's shared memory (N=%d, m=%d).", N_, m_);
+    /* Shared-memory plan: the longest look-ahead window K whose cross-term table stays below 48 KiB (tables grow with
+     * T K^2), and for it the deepest TMA ring that fits (12 dot warps x `stages` chunks of up to 4 KiB in flight). */
+    int chunkElems = 0, stages = 0, K = 0;
+    {
+        const int forceK = getenv("SQAOD_B200_SWEEP_K") ? atoi(getenv("SQAOD_B200_SWEEP_K")) : 0;       /* tuning aids */
+        const int forceS = getenv("SQAOD_B200_SWEEP_STAGES") ? atoi(getenv("SQAOD_B200_SWEEP_STAGES")) : 0;
+        const int chMax = std::min((int)ldJ_, (int)(4096 / sizeof(real)));
+        for (int k = SW_MAX_K; k >= 4 && K == 0; k >>= 1) {
+            if (forceK ? (k != forceK) : (k > 4 && (size_t)2 * maxT * k * 2 * k * sizeof(real) > (size_t)48 * 1024)) continue;
+            size_t bestRing = 0;
+            for (int ci = 0; ci < 4; ++ci) { /* the whole row (or 4 KiB of it), else a smaller power of two; multiples of 128 elements */
+                const int ch = (ci == 0) ? chMax : (int)(4096 / sizeof(real)) >> ci;
+                if (ch < 128 || (ci > 0 && ch >= chMax)) continue;
+                for (int st = 4; st >= 2; --st) {
+                    if (forceS && st != forceS) continue;
+                    if (SweepSmem<real>(maxT, nw64, ch, st, k).total > dev_->smemPerBlockOptin()) continue;
+                    const size_t ringBytes = (size_t)SW_DOT_WARPS * st * ch * sizeof(real);
+                    if (ringBytes > bestRing) { bestRing = ringBytes; K = k; chunkElems = ch; stages = st; }
+                }
+            }
+        }
+        sqb_throwErrorIf(K == 0, "problem too large for the sweep kernel's shared memory (N=%d, m=%d).", N_, m_);
     }
     K_ = K;
     grid_ = G;

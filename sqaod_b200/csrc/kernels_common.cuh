@@ -77,6 +77,16 @@ __device__ __forceinline__ void ldsReal(uint32_t a, float &v) { asm volatile("ld
 __device__ __forceinline__ void ldsReal(uint32_t a, double &v) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); }
 __device__ __forceinline__ void stsReal(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void stsReal(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+/* CTA-scope release / acquire on 32-bit counters in shared memory (hand-offs between the warps of the sweep kernel) */
+__device__ __forceinline__ uint32_t ldAcquireCta(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stReleaseCta(uint32_t a, uint32_t v) { asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void redAddReleaseCta(uint32_t a, uint32_t v) {
+    asm volatile("red.release.cta.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 /* named barrier over `count` threads (a multiple of 32) of the CTA; warps may arrive from different code paths */
 __device__ __forceinline__ void namedBarSync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 

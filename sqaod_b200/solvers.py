@@ -198,7 +198,8 @@ class DenseGraphAnnealer(_SolverBase):
         raw = (C.c_ulonglong * 8)()
         _lib.check(L.sqb_dg_annealer_get_counters(self._cobj, raw, self._dt))
         return {'accepted': a.value, 'flag_waits': w.value, 'barrier_cycles_dot': d.value, 'barrier_cycles_chain': c.value,
-                'helper_cycles': raw[5], 'prep_cycles': raw[6]}
+                'helper_cycles': raw[5], 'prep_cycles': raw[6],
+                'chain_wait_rows_cycles': raw[4], 'chain_wait_neighbour_cycles': raw[7]}
 
 
 def dense_graph_annealer(W=None, optimize=minimize, dtype=np.float64, device=None, **prefs):

@@ -12,17 +12,24 @@
  *
  * ONE persistent cooperative kernel per annealOneStep (the reference needs 2N dependent launches):
  *   - CTA c owns T contiguous trotters (m spread over min(#SM, m) CTAs); their spins live bit-packed in shared memory.
- *   - 8 "dot" warps stream the J rows the owned trotters will need, K=16 rounds ahead of the accept chain, through
- *     per-warp rings of TMA bulk copies (cp.async.bulk + mbarrier), and reduce sum_j J_xj q_yj against a SNAPSHOT of
- *     q_y with warp shuffles.  Flip positions are state-independent, so rows are known arbitrarily far ahead.
+ *   - 12 "dot" warps (those with warp & 3 != 0, i.e. three of the SM's four schedulers) stream the J rows the owned
+ *     trotters will need, one window of K <= 16 rounds ahead of the accept chain, through per-warp rings of TMA bulk
+ *     copies (cp.async.bulk + mbarrier), and reduce sum_j J_xj q_yj against a SNAPSHOT of q_y with warp shuffles.
+ *     Flip positions are state-independent (Philox), so rows are known arbitrarily far ahead; rows are claimed from a
+ *     shared counter.
  *   - because at most one spin per trotter changes per round, the dot product against the stale snapshot is repaired
  *     exactly with one term per accepted flip since the snapshot: -2 q_old[x'] J[x][x'].  The J[x][x'] cross terms are
  *     picked out of the row while it sits in shared memory (one per lane, <= 2K-1 = 31 of them).
- *   - 1 "chain" warp (lane = trotter) replays the K rounds in the reference's order using the finished dot products,
- *     the cross terms and the neighbours' spins.  Neighbours inside the CTA are read from shared memory; for the two
- *     trotters owned by other CTAs the chain uses a published snapshot plus the accept bits of exactly those
- *     neighbour attempts that hit the same spin index (probability ~K/N per attempt), so there is no per-round grid
- *     barrier: CTAs meet only through per-window snapshots and rare per-attempt flag waits (L2, release/acquire).
+ *   - 1 "chain" warp (lane = trotter), alone on scheduler 0 with three light helper warps, replays the K rounds in the
+ *     reference's order using the finished dot products, the cross terms and the neighbours' spins.  Neighbours inside
+ *     the CTA are read from shared memory; for the two trotters owned by other CTAs the chain uses a published
+ *     snapshot plus the accept bits of exactly those neighbour attempts that hit the same spin index (probability
+ *     ~K/N per attempt), so there is no per-round grid barrier: CTAs meet only through per-window snapshots and rare
+ *     per-attempt flag waits (L2, release/acquire).
+ *   - helper warps: "snapshot" (builds S_w from the window's accept bits, publishes the edge trotters), "neighbour"
+ *     (fetches the neighbours' snapshots, builds the conflict masks), "prep" (Philox tables two windows ahead).
+ *   - inside the CTA there is no barrier in the sweep either: the warps hand work over through five release/acquire
+ *     counters in shared memory (see the kernel body).
  * HBM traffic is one J row per attempt (N*sizeof(real) bytes), the figure SURVEY.md section 8(d) uses.
  */
 #include "device.hpp"
@@ -244,8 +251,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 const int sl = lane ? slotR : slotL;
                 const unsigned long long want = P.snapBase + (unsigned long long)(wn - 1);
                 const long long t0 = clock64();
-                if (ringSharded) { while (ldAcquireSys(sFlags + sl) < want) { ++nWaits; __nanosleep(20); } }
-                else { while (ldAcquire(sFlags + sl) < want) { ++nWaits; __nanosleep(20); } }
+                unsigned ns = 20;
+                if (ringSharded) { while (ldAcquireSys(sFlags + sl) < want) { ++nWaits; __nanosleep(ns); if (ns < 640u) ns <<= 1; } }
+                else { while (ldAcquire(sFlags + sl) < want) { ++nWaits; __nanosleep(ns); if (ns < 640u) ns <<= 1; } }
                 if (lane == 0) waited += clock64() - t0;
             }
             __syncwarp();
@@ -336,10 +344,15 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
      * replayed, one full window before the chain needs them. */
     const uint32_t aSync = smemAddr(taskCounter);
     const uint32_t aRowsDone = aSync + 4, aReplayDone = aSync + 12, aSnapCount = aSync + 16, aNbCount = aSync + 20, aPrepCount = aSync + 24;
-    auto waitCount = [&](uint32_t addr, uint32_t want, unsigned ns) { /* whole warp; lane 0 polls */
+    auto waitCount = [&](uint32_t addr, uint32_t want, unsigned ns) { /* whole warp; lane 0 polls, backing off to 16 ns */
         if (lane == 0 && ldAcquireCta(addr) < want) {
             const long long t0 = clock64();
-            while (ldAcquireCta(addr) < want) { if (ns) __nanosleep(ns); }
+            const unsigned nsMax = (ns ? ns : 16u) * 16u;
+            unsigned polls = 0;
+            while (ldAcquireCta(addr) < want) {
+                if (ns) { __nanosleep(ns); if (ns < nsMax) ns <<= 1; }
+                else if (++polls >= 16u) ns = 16u; /* a short spin first: the chain's waits are usually a few hundred cycles */
+            }
             waited += clock64() - t0;
         }
         __syncwarp();

@@ -213,7 +213,7 @@ def main():
         ann.set_qset(q_host)                    # H2D of the spin matrix (pinned), m x N int8
         ann.anneal_one_step(G_FIXED, BETA)
         E = ann.get_E()                         # energy kernel + D2H of m reals
-        q_host[...] = ann.get_spins()           # D2H of the spin matrix
+        ann.get_spins(out=q_host)               # D2H of the spin matrix into the pinned buffer
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device='cuda')

@@ -456,7 +456,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     __syncthreads();
     const long long tLoop0 = clock64();
 
-    if (dotWarp) {
+    /* CTAs with fewer trotters than the heaviest ones keep proportionally fewer rows in flight: when the sweep is bound by
+     * HBM, bandwidth is shared in proportion to the bytes each SM has outstanding, and all CTAs should finish a window at
+     * the same time (512 trotters on 148 SMs: 4 or 3 per CTA -> 12 or 9 streaming warps). */
+    const int activeDotWarps = max(1, (SW_DOT_WARPS * T + maxT - 1) / maxT);
+    if (dotWarp && dw < activeDotWarps) {
         if (lane == 0)
             for (int s = 0; s < S; ++s) issueNext();
         int curW = -1;

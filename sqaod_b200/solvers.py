@@ -147,9 +147,14 @@ class DenseGraphAnnealer(_SolverBase):
     def get_q(self):
         return self._bits(L.sqb_dg_annealer_get_q)
 
-    def get_spins(self):
-        """m x N int8 matrix straight from the device (no solution-list bookkeeping)."""
-        out = np.empty((self._m(), self.get_problem_size()), np.int8)
+    def get_spins(self, out=None):
+        """m x N int8 matrix straight from the device (no solution-list bookkeeping); `out` may be a caller-owned
+        (e.g. pinned) C-contiguous int8 array of that shape, which is then filled in place."""
+        shape = (self._m(), self.get_problem_size())
+        if out is None:
+            out = np.empty(shape, np.int8)
+        elif out.shape != shape or out.dtype != np.int8 or not out.flags.c_contiguous:
+            raise ValueError('out must be a C-contiguous int8 array of shape %s' % (shape,))
         _lib.check(L.sqb_dg_annealer_get_spins(self._cobj, ptr(out), self._dt))
         return out
 
@@ -158,7 +163,10 @@ class DenseGraphAnnealer(_SolverBase):
         _lib.check(L.sqb_dg_annealer_set_q(self._cobj, ptr(q), q.shape[0], self._dt))
 
     def set_qset(self, qset):
-        q = np.ascontiguousarray(np.stack([np.asarray(v, np.int8) for v in qset]))
+        if isinstance(qset, np.ndarray) and qset.ndim == 2 and qset.dtype == np.int8 and qset.flags.c_contiguous:
+            q = qset            # already an m x N int8 matrix (possibly pinned): copied to the device as it is
+        else:
+            q = np.ascontiguousarray(np.stack([np.asarray(v, np.int8) for v in qset]))
         _lib.check(L.sqb_dg_annealer_set_qset(self._cobj, ptr(q), q.shape[0], q.shape[1], self._dt))
 
     def randomize_spin(self):

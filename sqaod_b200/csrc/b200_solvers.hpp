@@ -105,6 +105,7 @@ private:
     real c_;
     unsigned long long seed_, step_, randomizeCount_, launchCount_;
     int grid_, chunkElems_, chunksPerRow_, stages_, nw64_, nWindows_, K_;
+    int dotWarps_ = 12;
     size_t smemBytes_;
     mutable unsigned long long lastBarrierWaitDot_ = 0, lastBarrierWaitChain_ = 0;
     HostVector E_;

@@ -45,7 +45,7 @@
 
 namespace sqb {
 
-enum { SW_MAX_K = 16, SW_DOT_WARPS = 12, SW_THREADS = 512, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4, SW_TAB_SLOTS = 4,
+enum { SW_MAX_K = 16, SW_DOT_WARPS = 12 /* chain-critical layout */, SW_DOT_WARPS_WIDE = 14 /* many trotters per CTA */, SW_THREADS = 512, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4, SW_TAB_SLOTS = 4,
        SW_CHAIN_WARP = 0, SW_SNAP_WARP = 4, SW_PREP_WARP = 8, SW_NB_WARP = 12 /* the dot warps are those with warp & 3 != 0 */ };
 
 template <class real> struct SweepParams {
@@ -57,6 +57,7 @@ template <class real> struct SweepParams {
     real twoDivM, coef, beta;
     real scaleA, scaleNb; /* accept iff q (scaleA (h + 2 sum) - scaleNb (ql + qr)) < -ln u : scaleA = beta 2/m (SA: 2/kT), scaleNb = beta coef */
     int chunkElems, chunksPerRow, stages, nw64, K;
+    int dotWarps; /* SW_DOT_WARPS: chain alone on scheduler 0; SW_DOT_WARPS_WIDE: warps 4 and 8 stream too, warp 12 does all the helper work */
     /* hand-off arrays have m + 2 slots: local trotter l -> slot l; slot m / m + 1 = the trotter left of local 0 / right of
      * local m-1 when it lives on another GPU (ring sharding); the owning GPU mirrors its publications into them */
     unsigned long long *acceptFlags; /* [m+2][SW_FLAG_RING] */
@@ -78,10 +79,10 @@ template <class real> struct SweepParams {
 /* shared-memory carve-up, identical on host and device */
 template <class real> struct SweepSmem {
     size_t ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, confAny, accLog, counter, total;
-    __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K) {
+    __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K, int dotWarps) {
         size_t o = 0;
-        ring = o; o += (size_t)SW_DOT_WARPS * stages * chunkElems * sizeof(real);
-        bars = o; o += (size_t)SW_DOT_WARPS * stages * 8;
+        ring = o; o += (size_t)dotWarps * stages * chunkElems * sizeof(real);
+        bars = o; o += (size_t)dotWarps * stages * 8;
         qcur = o; o += (size_t)T * nw64 * 8;
         qsnap = o; o += (size_t)2 * T * nw64 * 8;
         nbsnap = o; o += (size_t)2 * 2 * nw64 * 8;
@@ -160,9 +161,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     /* warp roles.  Warps are spread over the SM's four schedulers by (warp & 3): scheduler 0 is kept for the latency-bound
      * accept chain and its helpers, the twelve streaming dot warps share the other three. */
-    const bool dotWarp = (warp & 3) != 0;
-    const int dw = (warp >> 2) * 3 + (warp & 3) - 1; /* dot warp index 0..11 */
-    const bool chainWarp = (warp == SW_CHAIN_WARP), snapWarp = (warp == SW_SNAP_WARP), prepWarp = (warp == SW_PREP_WARP), nbWarp = (warp == SW_NB_WARP);
+    const bool wide = (P.dotWarps == SW_DOT_WARPS_WIDE);
+    const bool dotWarp = (warp & 3) != 0 || (wide && (warp == SW_SNAP_WARP || warp == SW_PREP_WARP));
+    /* dot warp index: 0..11 for the warps of schedulers 1-3, 12 / 13 for warps 4 / 8 in the wide layout */
+    const int dw = (warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : SW_DOT_WARPS + (warp >> 2) - 1;
+    const bool chainWarp = (warp == SW_CHAIN_WARP);
+    const bool snapWarp = !wide && (warp == SW_SNAP_WARP), prepWarp = !wide && (warp == SW_PREP_WARP), nbWarp = !wide && (warp == SW_NB_WARP);
+    const bool allHelperWarp = wide && (warp == SW_NB_WARP); /* wide layout: warp 12 builds snapshots, tables and neighbour data in turn */
     const int N = P.N, m = P.m;
     const int G = gridDim.x, cta = blockIdx.x;
     const int baseT = m / G, remT = m % G;
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     const int CH = P.chunkElems, CPR = P.chunksPerRow, S = P.stages, NW = P.nw64;
     const int GPC = CH >> 7;
 
-    const SweepSmem<real> L(maxT, NW, CH, S, K);
+    const SweepSmem<real> L(maxT, NW, CH, S, K, P.dotWarps);
     real *ring = reinterpret_cast<real *>(smem + L.ring);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
     unsigned long long *qcur = reinterpret_cast<unsigned long long *>(smem + L.qcur);
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     for (int i = tid; i < 4 * NW; i += SW_THREADS) nbsnap[i] = 0ull;
     if (tid == 0) {
         *taskCounter = 0u;
-        for (int i = 0; i < SW_DOT_WARPS * S; ++i) mbarInit(&bars[i], 1);
+        for (int i = 0; i < P.dotWarps * S; ++i) mbarInit(&bars[i], 1);
         mbarInitFence();
     }
     __syncthreads();
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     __syncthreads();
     for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
     for (int i = tid; i < 2 * NW; i += SW_THREADS) nbsnap[2 * NW + i] = nbsnap[i]; /* windows 0 and 1 both start from S_0 */
-    if (nbWarp) neighbourWindow(0);
+    if (warp == SW_NB_WARP) neighbourWindow(0);
 
     /* ---------------- hand-off counters between the warps of this CTA (shared memory, release/acquire at CTA scope) ------
      * There is no CTA-wide barrier inside the sweep: every warp runs its own loop over the windows and waits only for what it
@@ -449,6 +454,56 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         if (lane == 0) redAddReleaseCta(aRowsDone + 4u * (uint32_t)buf, 1u);
     };
 
+    /* S_w for the dot warps (shared memory, double buffered) and for the neighbouring CTAs (global memory) */
+    auto snapshotWindow = [&](int w) {
+        {   /* S_w = S_{w-1} with the accepted flips of window w-1 */
+            const unsigned long long *src = qsnap + (size_t)((w - 1) & 1) * maxT * NW;
+            unsigned long long *dst = qsnap + (size_t)(w & 1) * maxT * NW;
+            for (int i = lane; i < T * NW; i += 32) dst[i] = src[i];
+            __syncwarp();
+            if (lane < T) {
+                uint32_t bitsAcc = accLog[((w - 1) & 1) * maxT + lane];
+                const int *xbRow = xb + (((w - 1) & (SW_TAB_SLOTS - 1)) * maxT + lane) * K;
+                uint32_t *row = reinterpret_cast<uint32_t *>(dst + (size_t)lane * NW);
+                while (bitsAcc) {
+                    const int rl = __ffs(bitsAcc) - 1;
+                    bitsAcc &= bitsAcc - 1;
+                    const int xbv = xbRow[rl];
+                    row[xbv >> 5] ^= 1u << (xbv & 31);
+                }
+            }
+        }
+        signalCount(aSnapCount, (uint32_t)w + 1u);
+        if (remote) { /* publish the edge trotters' S_w for the neighbouring CTAs */
+            const unsigned long long *snapW = qsnap + (size_t)(w & 1) * maxT * NW;
+            const int nEdge = (T > 1) ? 2 : 1;
+            for (int i = lane; i < nEdge * NW; i += 32) {
+                const int e = i / NW, k = i - e * NW;
+                const int t = e ? T - 1 : 0;
+                const unsigned long long v = snapW[(size_t)t * NW + k];
+                const size_t off = (size_t)(w % SW_SNAP_SLOTS) * NW + k;
+                sBits[(size_t)(y0 + t) * SW_SNAP_SLOTS * NW + off] = v;
+                if (ringSharded) {
+                    if (y0 + t == 0 && P.peerSnapBits[0]) P.peerSnapBits[0][(size_t)(m + 1) * SW_SNAP_SLOTS * NW + off] = v;
+                    if (y0 + t == m - 1 && P.peerSnapBits[1]) P.peerSnapBits[1][(size_t)m * SW_SNAP_SLOTS * NW + off] = v;
+                }
+            }
+            /* the warp barrier orders every lane's stores before lane 0's release (cumulative), so no per-lane
+             * fence is needed inside the GPU; across GPUs keep the explicit system fence */
+            if (ringSharded) __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned long long sv = P.snapBase + (unsigned long long)w;
+                stRelease(sFlags + y0, sv);
+                if (T > 1) stRelease(sFlags + y0 + T - 1, sv);
+                if (ringSharded) {
+                    if (y0 == 0 && P.peerSnapFlags[0]) stReleaseSys(P.peerSnapFlags[0] + m + 1, sv);
+                    if (y0 + T == m && P.peerSnapFlags[1]) stReleaseSys(P.peerSnapFlags[1] + m, sv);
+                }
+            }
+        }
+    };
+
     if (tid == 0) {
         stReleaseCta(aRowsDone, 0u); stReleaseCta(aRowsDone + 4, 0u); stReleaseCta(aReplayDone, 0u);
         stReleaseCta(aSnapCount, 1u); stReleaseCta(aNbCount, 1u); stReleaseCta(aPrepCount, 3u);
@@ -459,7 +514,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     /* CTAs with fewer trotters than the heaviest ones keep proportionally fewer rows in flight: when the sweep is bound by
      * HBM, bandwidth is shared in proportion to the bytes each SM has outstanding, and all CTAs should finish a window at
      * the same time (512 trotters on 148 SMs: 4 or 3 per CTA -> 12 or 9 streaming warps). */
-    const int activeDotWarps = max(1, (SW_DOT_WARPS * T + maxT - 1) / maxT);
+    const int activeDotWarps = max(1, (P.dotWarps * T + maxT - 1) / maxT);
     if (dotWarp && dw < activeDotWarps) {
         if (lane == 0)
             for (int s = 0; s < S; ++s) issueNext();
@@ -476,55 +531,19 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             dotRow(g, w);
         }
     } else if (snapWarp) {
-        /* S_w for the dot warps and for the neighbouring CTAs, as soon as window w-1 has been replayed */
+        for (int w = 1; w < nW; ++w) { /* as soon as window w-1 has been replayed */
+            waitCount(aReplayDone, (uint32_t)w, 20);
+            snapshotWindow(w);
+        }
+    } else if (allHelperWarp) {
+        /* wide layout: after window w-1 has been replayed -- S_w, then the tables of window w+2 (slot of window w-2, dead
+         * once S_w exists), then the neighbour data of window w+1 */
+        if (1 < nW) { neighbourWindow(1); signalCount(aNbCount, 2u); }
         for (int w = 1; w < nW; ++w) {
             waitCount(aReplayDone, (uint32_t)w, 20);
-            {   /* S_w = S_{w-1} with the accepted flips of window w-1 */
-                const unsigned long long *src = qsnap + (size_t)((w - 1) & 1) * maxT * NW;
-                unsigned long long *dst = qsnap + (size_t)(w & 1) * maxT * NW;
-                for (int i = lane; i < T * NW; i += 32) dst[i] = src[i];
-                __syncwarp();
-                if (lane < T) {
-                    uint32_t bitsAcc = accLog[((w - 1) & 1) * maxT + lane];
-                    const int *xbRow = xb + (((w - 1) & (SW_TAB_SLOTS - 1)) * maxT + lane) * K;
-                    uint32_t *row = reinterpret_cast<uint32_t *>(dst + (size_t)lane * NW);
-                    while (bitsAcc) {
-                        const int rl = __ffs(bitsAcc) - 1;
-                        bitsAcc &= bitsAcc - 1;
-                        const int xbv = xbRow[rl];
-                        row[xbv >> 5] ^= 1u << (xbv & 31);
-                    }
-                }
-            }
-            signalCount(aSnapCount, (uint32_t)w + 1u);
-            if (remote) { /* publish the edge trotters' S_w for the neighbouring CTAs */
-                const unsigned long long *snapW = qsnap + (size_t)(w & 1) * maxT * NW;
-                const int nEdge = (T > 1) ? 2 : 1;
-                for (int i = lane; i < nEdge * NW; i += 32) {
-                    const int e = i / NW, k = i - e * NW;
-                    const int t = e ? T - 1 : 0;
-                    const unsigned long long v = snapW[(size_t)t * NW + k];
-                    const size_t off = (size_t)(w % SW_SNAP_SLOTS) * NW + k;
-                    sBits[(size_t)(y0 + t) * SW_SNAP_SLOTS * NW + off] = v;
-                    if (ringSharded) {
-                        if (y0 + t == 0 && P.peerSnapBits[0]) P.peerSnapBits[0][(size_t)(m + 1) * SW_SNAP_SLOTS * NW + off] = v;
-                        if (y0 + t == m - 1 && P.peerSnapBits[1]) P.peerSnapBits[1][(size_t)m * SW_SNAP_SLOTS * NW + off] = v;
-                    }
-                }
-                /* the warp barrier orders every lane's stores before lane 0's release (cumulative), so no per-lane
-                 * fence is needed inside the GPU; across GPUs keep the explicit system fence */
-                if (ringSharded) __threadfence_system();
-                __syncwarp();
-                if (lane == 0) {
-                    const unsigned long long sv = P.snapBase + (unsigned long long)w;
-                    stRelease(sFlags + y0, sv);
-                    if (T > 1) stRelease(sFlags + y0 + T - 1, sv);
-                    if (ringSharded) {
-                        if (y0 == 0 && P.peerSnapFlags[0]) stReleaseSys(P.peerSnapFlags[0] + m + 1, sv);
-                        if (y0 + T == m && P.peerSnapFlags[1]) stReleaseSys(P.peerSnapFlags[1] + m, sv);
-                    }
-                }
-            }
+            snapshotWindow(w);
+            if (w + 2 < nW) { prepWindow(w + 2, lane, 32); signalCount(aPrepCount, (uint32_t)w + 3u); }
+            if (w + 1 < nW) { neighbourWindow(w + 1); signalCount(aNbCount, (uint32_t)w + 2u); }
         }
     } else if (nbWarp) {
         /* the neighbours' S_{wn-1} and the conflict masks of window wn, into the buffers window wn-2 has finished with */
@@ -744,7 +763,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             if (nWaits) atomicAdd(P.stats + 1, nWaits);
             if (dotWarp && dw == 0) atomicAdd(P.stats + 2, (unsigned long long)busy); /* dot warp 0: cycles spent on dot products */
             if (chainWarp) atomicAdd(P.stats + 3, (unsigned long long)busy);          /* chain warp: cycles spent replaying */
-            if (snapWarp || nbWarp) atomicAdd(P.stats + 5, (unsigned long long)busy); /* snapshot + neighbour warps */
+            if (snapWarp || nbWarp || allHelperWarp) atomicAdd(P.stats + 5, (unsigned long long)busy); /* snapshot + neighbour (or all-helper) warps */
             if (prepWarp) atomicAdd(P.stats + 6, (unsigned long long)busy);           /* prep warp: Philox tables */
         }
     }
@@ -965,6 +984,10 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     const int nw64 = packedWords64(N_);
     /* Shared-memory plan: the longest look-ahead window K whose cross-term table stays below 48 KiB (tables grow with
      * T K^2), and for it the deepest TMA ring that fits (12 dot warps x `stages` chunks of up to 4 KiB in flight). */
+    /* warp layout: from three trotters per CTA on the accept chain is no longer what bounds the step (measured), and two
+     * more warps stream rows */
+    dotWarps_ = (maxT >= 3) ? SW_DOT_WARPS_WIDE : SW_DOT_WARPS;
+    if (getenv("SQAOD_B200_SWEEP_WIDE")) dotWarps_ = atoi(getenv("SQAOD_B200_SWEEP_WIDE")) ? SW_DOT_WARPS_WIDE : SW_DOT_WARPS;
     int chunkElems = 0, stages = 0, K = 0;
     {
         const int forceK = getenv("SQAOD_B200_SWEEP_K") ? atoi(getenv("SQAOD_B200_SWEEP_K")) : 0;       /* tuning aids */
@@ -978,8 +1001,8 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
                 if (ch < 128 || (ci > 0 && ch >= chMax)) continue;
                 for (int st = 4; st >= 2; --st) {
                     if (forceS && st != forceS) continue;
-                    if (SweepSmem<real>(maxT, nw64, ch, st, k).total > dev_->smemPerBlockOptin()) continue;
-                    const size_t ringBytes = (size_t)SW_DOT_WARPS * st * ch * sizeof(real);
+                    if (SweepSmem<real>(maxT, nw64, ch, st, k, dotWarps_).total > dev_->smemPerBlockOptin()) continue;
+                    const size_t ringBytes = (size_t)dotWarps_ * st * ch * sizeof(real);
                     if (ringBytes > bestRing) { bestRing = ringBytes; K = k; chunkElems = ch; stages = st; }
                 }
             }
@@ -992,7 +1015,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     chunksPerRow_ = (ldJ_ + chunkElems - 1) / chunkElems;
     stages_ = stages;
     nw64_ = nw64;
-    smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages, K).total;
+    smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages, K, dotWarps_).total;
     nWindows_ = (N_ + K - 1) / K;
     allocHandoff();
     dStats_.alloc(dev_, 8);
@@ -1150,7 +1173,7 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
         P.scaleA = real(2.) * P.beta;
         P.scaleNb = real(0.);
     }
-    P.chunkElems = chunkElems_; P.chunksPerRow = chunksPerRow_; P.stages = stages_; P.nw64 = nw64_; P.K = K_;
+    P.chunkElems = chunkElems_; P.chunksPerRow = chunksPerRow_; P.stages = stages_; P.nw64 = nw64_; P.K = K_; P.dotWarps = dotWarps_;
     HandoffLayout hl(m_, nw64_, ldq_);
     unsigned char *hb = (unsigned char *)handoff_;
     P.acceptFlags = (unsigned long long *)(hb + hl.flags); P.snapFlags = (unsigned long long *)(hb + hl.snapFlags);

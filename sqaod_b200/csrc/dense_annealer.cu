@@ -12,7 +12,7 @@
  *
  * ONE persistent cooperative kernel per annealOneStep (the reference needs 2N dependent launches):
  *   - CTA c owns T contiguous trotters (m spread over min(#SM, m) CTAs); their spins live bit-packed in shared memory.
- *   - 12 "dot" warps (those with warp & 3 != 0, i.e. three of the SM's four schedulers) stream the J rows the owned
+ *   - 12 or 14 "dot" warps stream the J rows the owned
  *     trotters will need, one window of K <= 16 rounds ahead of the accept chain, through per-warp rings of TMA bulk
  *     copies (cp.async.bulk + mbarrier), and reduce sum_j J_xj q_yj against a SNAPSHOT of q_y with warp shuffles.
  *     Flip positions are state-independent (Philox), so rows are known arbitrarily far ahead; rows are claimed from a
@@ -20,14 +20,18 @@
  *   - because at most one spin per trotter changes per round, the dot product against the stale snapshot is repaired
  *     exactly with one term per accepted flip since the snapshot: -2 q_old[x'] J[x][x'].  The J[x][x'] cross terms are
  *     picked out of the row while it sits in shared memory (one per lane, <= 2K-1 = 31 of them).
- *   - 1 "chain" warp (lane = trotter), alone on scheduler 0 with three light helper warps, replays the K rounds in the
+ *   - 1 "chain" warp (lane = trotter) replays the K rounds in the
  *     reference's order using the finished dot products, the cross terms and the neighbours' spins.  Neighbours inside
  *     the CTA are read from shared memory; for the two trotters owned by other CTAs the chain uses a published
  *     snapshot plus the accept bits of exactly those neighbour attempts that hit the same spin index (probability
  *     ~K/N per attempt), so there is no per-round grid barrier: CTAs meet only through per-window snapshots and rare
  *     per-attempt flag waits (L2, release/acquire).
- *   - helper warps: "snapshot" (builds S_w from the window's accept bits, publishes the edge trotters), "neighbour"
+ *   - helper roles: "snapshot" (builds S_w from the window's accept bits, publishes the edge trotters), "neighbour"
  *     (fetches the neighbours' snapshots, builds the conflict masks), "prep" (Philox tables two windows ahead).
+ *   - two warp layouts (prepare() picks one from the trotters per CTA): up to 2 trotters per CTA the chain bounds the
+ *     step, so warp 0 (chain) shares its scheduler only with the three helper warps 4 / 8 / 12 and the 12 dot warps are
+ *     those of the other three schedulers; from 3 trotters per CTA on, warps 4 and 8 stream rows too (14 dot warps) and
+ *     warp 12 does the three helper jobs in turn.
  *   - inside the CTA there is no barrier in the sweep either: the warps hand work over through five release/acquire
  *     counters in shared memory (see the kernel body).
  * HBM traffic is one J row per attempt (N*sizeof(real) bytes), the figure SURVEY.md section 8(d) uses.

@@ -127,23 +127,47 @@ template <class real> __device__ __forceinline__ real expReal(real v);
 template <> __device__ __forceinline__ float expReal<float>(float v) { return expf(v); }
 template <> __device__ __forceinline__ double expReal<double>(double v) { return exp(v); }
 
-/* accumulate the signed sum of one 128-spin group: lane owns 4 consecutive elements */
-__device__ __forceinline__ void accumGroup(const float *buf, uint32_t nib, float &a0, float &a1, float &a2, float &a3) {
+/* accumulate the signed sum of one 128-spin group: lane owns 4 consecutive elements.  The four fp32 accumulators are kept
+ * as two packed pairs so that the adds are `add.rn.f32x2` (SASS FADD2): same IEEE result per lane, half the add issue slots. */
+__device__ __forceinline__ unsigned long long packF32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void addF32x2(unsigned long long &acc, unsigned long long v) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(v)); }
+struct Acc4f { /* a0..a3 of the fp32 dot product */
+    unsigned long long a01, a23;
+    __device__ __forceinline__ Acc4f() : a01(0ull), a23(0ull) {}
+    __device__ __forceinline__ float sum() const {
+        float a0, a1, a2, a3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a01));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(a2), "=f"(a3) : "l"(a23));
+        return (a0 + a1) + (a2 + a3);
+    }
+};
+struct Acc4d {
+    double a0, a1, a2, a3;
+    __device__ __forceinline__ Acc4d() : a0(0.), a1(0.), a2(0.), a3(0.) {}
+    __device__ __forceinline__ double sum() const { return (a0 + a1) + (a2 + a3); }
+};
+template <class real> struct Acc4;
+template <> struct Acc4<float> { typedef Acc4f type; };
+template <> struct Acc4<double> { typedef Acc4d type; };
+
+__device__ __forceinline__ void accumGroup(const float *buf, uint32_t nib, Acc4f &a) {
     float4 v = *reinterpret_cast<const float4 *>(buf);
     uint32_t neg = ~nib; /* bit set -> spin +1 -> keep sign */
-    a0 += signFlip(v.x, neg << 31);
-    a1 += signFlip(v.y, neg << 30);
-    a2 += signFlip(v.z, neg << 29);
-    a3 += signFlip(v.w, neg << 28);
+    addF32x2(a.a01, packF32x2(signFlip(v.x, neg << 31), signFlip(v.y, neg << 30)));
+    addF32x2(a.a23, packF32x2(signFlip(v.z, neg << 29), signFlip(v.w, neg << 28)));
 }
-__device__ __forceinline__ void accumGroup(const double *buf, uint32_t nib, double &a0, double &a1, double &a2, double &a3) {
+__device__ __forceinline__ void accumGroup(const double *buf, uint32_t nib, Acc4d &a) {
     double2 v0 = *reinterpret_cast<const double2 *>(buf);
     double2 v1 = *reinterpret_cast<const double2 *>(buf + 2);
     uint32_t neg = ~nib;
-    a0 += signFlip(v0.x, neg << 31);
-    a1 += signFlip(v0.y, neg << 30);
-    a2 += signFlip(v1.x, neg << 29);
-    a3 += signFlip(v1.y, neg << 28);
+    a.a0 += signFlip(v0.x, neg << 31);
+    a.a1 += signFlip(v0.y, neg << 30);
+    a.a2 += signFlip(v1.x, neg << 29);
+    a.a3 += signFlip(v1.y, neg << 28);
 }
 
 __device__ __forceinline__ int sweepPhase(int y, int m) { /* 0: even, 1: trotter m-1 of an odd ring, 2: odd */
@@ -420,7 +444,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         if (lane < K) { if (w > 0) px = xs[(((w - 1) & (SW_TAB_SLOTS - 1)) * maxT + t) * K + lane]; }
         else if (lane < 2 * K && lane - K < rl) px = xs[(slot * maxT + t) * K + (lane - K)];
         real crossv = real(0);
-        real a0 = real(0), a1 = real(0), a2 = real(0), a3 = real(0);
+        typename Acc4<real>::type acc;
         const unsigned long long *qrow = qsnap + ((size_t)((w > 0) ? ((w - 1) & 1) : 0) * maxT + t) * NW;
         for (int c = 0; c < CPR; ++c) {
             mbarWait(&myBars[cStage], cParity);
@@ -433,15 +457,15 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             if (groups == 16) {
                 const uint32_t blo = (uint32_t)bits, bhi = (uint32_t)(bits >> 32);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) accumGroup(src + i * 128, (blo >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+                for (int i = 0; i < 8; ++i) accumGroup(src + i * 128, (blo >> (4 * i)) & 0xfu, acc);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) accumGroup(src + (i + 8) * 128, (bhi >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+                for (int i = 0; i < 8; ++i) accumGroup(src + (i + 8) * 128, (bhi >> (4 * i)) & 0xfu, acc);
             } else if (groups == 8) {
                 const uint32_t blo = (uint32_t)bits;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) accumGroup(src + i * 128, (blo >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+                for (int i = 0; i < 8; ++i) accumGroup(src + i * 128, (blo >> (4 * i)) & 0xfu, acc);
             } else {
-                for (int i = 0; i < groups; ++i) accumGroup(src + i * 128, (uint32_t)(bits >> (4 * i)) & 0xfu, a0, a1, a2, a3);
+                for (int i = 0; i < groups; ++i) accumGroup(src + i * 128, (uint32_t)(bits >> (4 * i)) & 0xfu, acc);
             }
             if (px >= c0 && px < c0 + (groups << 7)) crossv = buf_[px - c0];
             __syncwarp();
@@ -451,7 +475,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             }
             if (++cStage == S) { cStage = 0; cParity ^= 1u; }
         }
-        real s = warpSum((a0 + a1) + (a2 + a3));
+        real s = warpSum(acc.sum());
         if (lane == 0) dots[(buf * maxT + t) * K + rl] = P.scaleA * (hs[(slot * maxT + t) * K + rl] + real(2) * s);
         if (lane < 2 * K) cross[((buf * maxT + t) * K + rl) * (2 * K) + lane] = crossv;
         __syncwarp();

@@ -13,7 +13,8 @@
  * accumulated essentially exactly; the result is within an ulp or two of the fp32 GEMM and exact on quantised inputs.
  *
  * Structure (one CTA per 128 x 128 output tile, 192 threads):
- *   warp 0  : TMA producer -- cp.async.bulk.tensor.2d of 128x64 bf16 boxes (128B swizzle) of Q and of the A split
+ *   warp 0  : TMA producer -- per K block one 128x64 bf16 box (128B swizzle) of Q and one of each of the three planes of A
+ *             (64 KiB per stage, 3 stages)
  *   warp 1  : TMEM allocation + single-thread tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16) issue,
  *             tcgen05.commit -> mbarrier to recycle shared-memory stages and to hand the accumulator over
  *   warps 2-5: epilogue -- tcgen05.ld 32x32b.x32 of the accumulator, fp32 stores of C
@@ -29,8 +30,9 @@
 
 namespace sqb {
 
-enum { TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 5, TC_THREADS = 192, TC_TMEM_COLS = 512 /* 3 x 128 used */ };
-enum { TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2, TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 + 256 };
+enum { TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 192, TC_TMEM_COLS = 512 /* 3 x 128 used */ };
+/* one pipeline stage = one K block of Q and the same K block of the three planes of A: Q is fetched once, not once per plane */
+enum { TC_TILE_BYTES = TC_BN * TC_BK * 2, TC_STAGE_BYTES = (TC_BM + 3 * TC_BN) * TC_BK * 2, TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 + 256 };
 
 __device__ __forceinline__ void tma2D(void *smemDst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -71,7 +73,7 @@ tcSpinGemmKernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * TC_BN, m0 = blockIdx.x * TC_BM; /* batch tiles on grid.x (may exceed 65535 / 128 rows) */
-    const int numKB = 3 * kBlocksPerSplit;
+    const int numKB = kBlocksPerSplit;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbarInit(&fullBar[s], 1); mbarInit(&emptyBar[s], 1); }
@@ -95,10 +97,10 @@ tcSpinGemmKernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 const int s = kb % TC_STAGES;
                 if (kb >= TC_STAGES) mbarWait(&emptyBar[s], ((kb / TC_STAGES) - 1) & 1);
                 unsigned char *a = smem + s * TC_STAGE_BYTES, *b = a + TC_BM * TC_BK * 2;
-                const int split = kb / kBlocksPerSplit, kc = (kb % kBlocksPerSplit) * TC_BK;
+                const int kc = kb * TC_BK;
                 mbarArriveExpectTx(&fullBar[s], TC_STAGE_BYTES);
                 tma2D(a, &mapQ, kc, m0, &fullBar[s]);
-                tma2D(b, &mapB, kc, split * rowsPadB + n0, &fullBar[s]);
+                for (int split = 0; split < 3; ++split) tma2D(b + split * TC_TILE_BYTES, &mapB, kc, split * rowsPadB + n0, &fullBar[s]);
             }
         }
     } else if (warp == 1) {
@@ -110,12 +112,14 @@ tcSpinGemmKernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 mbarWait(&fullBar[s], (kb / TC_STAGES) & 1);
                 tcFenceAfter();
                 const unsigned char *a = smem + s * TC_STAGE_BYTES, *b = a + TC_BM * TC_BK * 2;
-                const uint64_t ad = umdesc(a), bd = umdesc(b);
+                const uint64_t ad = umdesc(a);
 #pragma unroll
-                const int split = kb / kBlocksPerSplit; /* hi / mid / lo -> accumulator columns 0 / 128 / 256 */
-                const uint32_t first = (kb % kBlocksPerSplit) == 0 ? 0u : 1u;
-                for (int k = 0; k < TC_BK / 16; ++k) /* +32 bytes per K=16 step inside the 128-byte swizzle row */
-                    umma(tmemBase + (uint32_t)(split * TC_BN), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (first | (uint32_t)k) ? 1u : 0u);
+                for (int split = 0; split < 3; ++split) { /* hi / mid / lo -> accumulator columns 0 / 128 / 256 */
+                    const uint64_t bd = umdesc(b + split * TC_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) /* +32 bytes per K=16 step inside the 128-byte swizzle row */
+                        umma(tmemBase + (uint32_t)(split * TC_BN), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                }
                 ummaCommit(&emptyBar[s]);
             }
             ummaCommit(tmemFullBar);

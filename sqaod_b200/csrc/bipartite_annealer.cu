@@ -119,6 +119,52 @@ __global__ void bgFlipKernel(signed char *Q, int ldq, const real *dEmat, int ldc
     if (thr > philoxUniform<real>(p)) row[i] = (signed char)(-row[i]);
 }
 
+/* One launch per half step: a block owns blockDim.x (4..32) spin indices of EVERY trotter, so the phases of the reference order (even
+ * trotters, [trotter m-1 of an odd ring], odd trotters) are separated by __syncthreads() instead of kernel boundaries.
+ * Same Philox stream and arithmetic as bgFlipKernel.  When `qbf` is given the new spins are also written as bf16
+ * ([.][ldbf]), the operand layout of the tcgen05 contraction of the next half step. */
+enum { BGF_THREADS = 1024 };
+template <class real, bool SQA>
+__global__ void __launch_bounds__(BGF_THREADS)
+bgFlipFusedKernel(signed char *Q, int ldq, const real *dEmat, int ldc, const real *h, int NA, int m, unsigned long long seed,
+                  unsigned long long step, unsigned domain, real twoDivM, real coef, real beta, unsigned short *qbf, int ldbf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, rowLanes = blockDim.y;
+    const bool ok = i < NA;
+    const real hi = ok ? h[i] : real(0);
+    auto attempt = [&](int y) {
+        if (!ok) return;
+        signed char *row = Q + (size_t)y * ldq;
+        signed char qi = row[i];
+        const real q = (real)qi;
+        real dE;
+        if (SQA) {
+            dE = twoDivM * q * (hi + dEmat[(size_t)y * ldc + i]);
+            const int n0 = (y + m - 1) % m, n1 = (y + 1) % m;
+            const real nb = (real)((int)Q[(size_t)n0 * ldq + i] + (int)Q[(size_t)n1 * ldq + i]);
+            dE -= q * nb * coef;
+        } else {
+            dE = real(2) * q * (hi + dEmat[(size_t)y * ldc + i]);
+        }
+        const real thr = (dE < real(0)) ? real(1) : expR<real>(-dE * beta);
+        const Philox4 p = sqbPhilox(seed, step, domain, (uint32_t)i, (uint32_t)y);
+        if (thr > philoxUniform<real>(p)) {
+            qi = (signed char)(-qi);
+            row[i] = qi;
+        }
+        if (qbf) qbf[(size_t)y * ldbf + i] = (qi > 0) ? (unsigned short)0x3f80 : (unsigned short)0xbf80; /* +-1 in bf16 */
+    };
+    if (!SQA) {
+        for (int y = threadIdx.y; y < m; y += rowLanes) attempt(y);
+        return;
+    }
+    const int m2 = (m / 2) * 2;
+    for (int y = 2 * threadIdx.y; y < m2; y += 2 * rowLanes) attempt(y);
+    __syncthreads();
+    if ((m & 1) && threadIdx.y == 0) attempt(m - 1);
+    __syncthreads();
+    for (int y = 2 * threadIdx.y + 1; y < m2; y += 2 * rowLanes) attempt(y);
+}
+
 template <class real> __global__ void transposeMatKernel(real *T, int ldT, const real *A, int ldA, int rows, int cols) {
     __shared__ real tile[32][33];
     int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 32 + threadIdx.y;
@@ -179,6 +225,7 @@ public:
         ++dev_->launchCount;
         /* fp32: bf16 hi/mid/lo splits of J and J^T for the tcgen05 contraction (energy_tc.cu) */
         tcJ_.ready = tcJT_.ready = false;
+        qbfValid_[0] = qbfValid_[1] = false;
         if constexpr (std::is_same<real, float>::value) {
             if (tcEnabled()) {
                 tcPrepareOperand(*dev_, tcJ_, dJ_.p, ldJ_, N1_, N0_);
@@ -255,6 +302,7 @@ public:
         hq1_.assign((size_t)m_ * ldq1_, 0);
         xPairs_.clear();
         qPairs_.clear();
+        qbfValid_[0] = qbfValid_[1] = false;
         this->setState(Base::solPrepared);
     }
     void randomizeSpin() {
@@ -262,12 +310,14 @@ public:
         launchRandomizeSpin(*dev_, dq0_.p, ldq0_, N0_, m_, seed_, randomizeCount_, DOM_RANDOMIZE);
         launchRandomizeSpin(*dev_, dq1_.p, ldq1_, N1_, m_, seed_, randomizeCount_, DOM_RANDOMIZE1);
         ++randomizeCount_;
+        qbfValid_[0] = qbfValid_[1] = false;
         this->setState(Base::solQSet);
     }
     void uploadSpins() {
         dev_->h2d(dq0_.p, hq0_.data(), hq0_.size());
         dev_->h2d(dq1_.p, hq1_.data(), hq1_.size());
         dev_->synchronize();
+        qbfValid_[0] = qbfValid_[1] = false;
     }
     void set_q(const sq::BitSetPair &qPair) {
         sqb_throwErrorIf(qPair.bits0.size != N0_ || qPair.bits1.size != N1_, "Dimension of q0/q1 does not match N0/N1.");
@@ -363,39 +413,39 @@ private:
         const real *h = side ? dh1_.p : dh0_.p;
         const unsigned dom = side ? DOM_BG_SIDE1 : DOM_BG_SIDE0;
         bool done = false;
+        unsigned short *bfOut = NULL; /* bf16 copy of the side being updated: operand of the next half step's contraction */
+        int ldbf = 0;
         if constexpr (std::is_same<real, float>::value) {
-            const TcOperand &op = side ? tcJ_ : tcJT_;
-            if (op.ready && tcEnabled()) {
-                tcSpinGemm(*dev_, ddE_.p, ldc_, op, qF, ldqF, m_, tcWs_);
+            const TcOperand &op = side ? tcJ_ : tcJT_;   /* contracts over the fixed side */
+            const TcOperand &opNext = side ? tcJT_ : tcJ_; /* the next half step contracts over this side */
+            if (op.ready && opNext.ready && tcEnabled()) {
+                const int f = 1 - side;
+                if (!qbfValid_[f]) { /* after set_q / randomize: rebuild; afterwards the flip kernel keeps it current */
+                    tcWidenSpins(*dev_, qbf_[f], op, qF, ldqF, m_);
+                    qbfValid_[f] = true;
+                }
+                tcSpinGemmBf16(*dev_, ddE_.p, ldc_, op, qbf_[f].p, m_);
+                const size_t need = (size_t)sq::roundUp(m_, 128) * opNext.Kp;
+                if (qbf_[side].n < need || qbf_[side].dev != dev_) { qbf_[side].alloc(dev_, need); qbfValid_[side] = false; }
+                bfOut = qbf_[side].p;
+                ldbf = opNext.Kp;
                 done = true;
             }
         }
         if (!done) devSpinGemm<real>(*dev_, ddE_.p, ldc_, Je, ldJe, qF, ldqF, m_, NA, NF);
         cudaStream_t st = dev_->stream();
-        const int bx = 128;
-        if (!sqa) {
-            bgFlipKernel<real, false><<<dim3((NA + bx - 1) / bx, m_), bx, 0, st>>>(qA, ldqA, ddE_.p, ldc_, h, NA, m_, 3, seed_, step_, dom,
-                                                                                  twoDivM, coef, beta);
-            ++dev_->launchCount;
-        } else {
-            const int m2 = (m_ / 2) * 2;
-            if (m2 > 0) {
-                bgFlipKernel<real, true><<<dim3((NA + bx - 1) / bx, m2 / 2), bx, 0, st>>>(qA, ldqA, ddE_.p, ldc_, h, NA, m_, 0, seed_, step_,
-                                                                                         dom, twoDivM, coef, beta);
-                ++dev_->launchCount;
-            }
-            if (m_ & 1) {
-                bgFlipKernel<real, true><<<dim3((NA + bx - 1) / bx, 1), bx, 0, st>>>(qA, ldqA, ddE_.p, ldc_, h, NA, m_, 1, seed_, step_, dom,
-                                                                                    twoDivM, coef, beta);
-                ++dev_->launchCount;
-            }
-            if (m2 > 0) {
-                bgFlipKernel<real, true><<<dim3((NA + bx - 1) / bx, m2 / 2), bx, 0, st>>>(qA, ldqA, ddE_.p, ldc_, h, NA, m_, 2, seed_, step_,
-                                                                                         dom, twoDivM, coef, beta);
-                ++dev_->launchCount;
-            }
-        }
+        int cols = 32; /* spin indices per block: fewer when the side is short, so that the grid still covers the device */
+        while (cols > 4 && (NA + cols - 1) / cols < dev_->numSMs()) cols >>= 1;
+        const dim3 grid((NA + cols - 1) / cols), block(cols, BGF_THREADS / cols);
+        if (!sqa)
+            bgFlipFusedKernel<real, false><<<grid, block, 0, st>>>(qA, ldqA, ddE_.p, ldc_, h, NA, m_, seed_, step_, dom, twoDivM, coef, beta,
+                                                                   bfOut, ldbf);
+        else
+            bgFlipFusedKernel<real, true><<<grid, block, 0, st>>>(qA, ldqA, ddE_.p, ldc_, h, NA, m_, seed_, step_, dom, twoDivM, coef, beta,
+                                                                  bfOut, ldbf);
+        ++dev_->launchCount;
         CUDA_CHECK(cudaGetLastError());
+        if (bfOut) qbfValid_[side] = true; /* every spin of this side has just been rewritten */
     }
     void syncBits() {
         xPairs_.clear();
@@ -423,6 +473,8 @@ private:
     sq::BitSetPairArray xPairs_, qPairs_;
     TcOperand tcJ_, tcJT_;
     TcWorkspace tcWs_;
+    DevBuf<unsigned short> qbf_[2]; /* bf16 copies of the two spin matrices (tcgen05 operand layout), kept current by the flip kernel */
+    bool qbfValid_[2] = {false, false};
 };
 
 } // namespace sqb

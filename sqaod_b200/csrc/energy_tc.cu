@@ -243,16 +243,21 @@ void tcPrepareOperand(const B200Device &dev, TcOperand &op, const float *d_A, in
     op.ready = true;
 }
 
-void tcSpinGemm(const B200Device &dev, float *d_C, int ldc, const TcOperand &B, const signed char *d_Q, int ldq, int m, TcWorkspace &ws) {
-    sqb_throwErrorIf(!B.ready, "tensor-core operand not prepared.");
+void tcWidenSpins(const B200Device &dev, DevBuf<unsigned short> &qbf, const TcOperand &B, const signed char *d_Q, int ldq, int m) {
     const int mPad = sq::roundUp(m, TC_BM); /* whole boxes: padding rows stay zero */
     const size_t need = (size_t)mPad * B.Kp;
-    if (ws.qbf.n < need || ws.qbf.dev != &dev) ws.qbf.alloc(&dev, need);
-    ws.dev = &dev;
+    if (qbf.n < need || qbf.dev != &dev) qbf.alloc(&dev, need);
     dim3 wgrid(m, (B.Kp + 127) / 128);
-    tcWidenSpinsKernel<<<wgrid, 128, 0, dev.stream()>>>((__nv_bfloat16 *)ws.qbf.p, B.Kp, d_Q, ldq, m, B.K);
+    tcWidenSpinsKernel<<<wgrid, 128, 0, dev.stream()>>>((__nv_bfloat16 *)qbf.p, B.Kp, d_Q, ldq, m, B.K);
+    CUDA_CHECK(cudaGetLastError());
+    ++dev.launchCount;
+}
+
+void tcSpinGemmBf16(const B200Device &dev, float *d_C, int ldc, const TcOperand &B, const unsigned short *d_Qbf, int m) {
+    sqb_throwErrorIf(!B.ready, "tensor-core operand not prepared.");
+    const int mPad = sq::roundUp(m, TC_BM);
     CUtensorMap mapQ;
-    makeMap(&mapQ, ws.qbf.p, mPad, B.Kp, TC_BM);
+    makeMap(&mapQ, const_cast<unsigned short *>(d_Qbf), mPad, B.Kp, TC_BM);
     static bool attrSet = false;
     if (!attrSet) {
         CUDA_CHECK(cudaFuncSetAttribute(tcSpinGemmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
@@ -262,7 +267,13 @@ void tcSpinGemm(const B200Device &dev, float *d_C, int ldc, const TcOperand &B, 
     tcSpinGemmKernel<<<grid, TC_THREADS, TC_SMEM_BYTES, dev.stream()>>>(mapQ, *(const CUtensorMap *)B.map, d_C, ldc, m, B.rows, B.rowsPad,
                                                                         B.Kp / TC_BK);
     CUDA_CHECK(cudaGetLastError());
-    dev.launchCount += 2;
+    ++dev.launchCount;
+}
+
+void tcSpinGemm(const B200Device &dev, float *d_C, int ldc, const TcOperand &B, const signed char *d_Q, int ldq, int m, TcWorkspace &ws) {
+    ws.dev = &dev;
+    tcWidenSpins(dev, ws.qbf, B, d_Q, ldq, m);
+    tcSpinGemmBf16(dev, d_C, ldc, B, ws.qbf.p, m);
 }
 
 /* E_b = alpha * ( sum_i v_bi (g_i + C_bi) + sum_j f_j u_bj ) + beta0, C = u . A^T from tcSpinGemm */

@@ -22,6 +22,10 @@ bool tcEnabled(); /* false when SQAOD_B200_NO_TC is set (A/B testing) or the dri
 void tcPrepareOperand(const B200Device &dev, TcOperand &op, const float *d_A, int ldA, int rows, int K);
 /* C[y][i] = sum_k Q[y][k] A[i][k],  y < m, i < A.rows */
 void tcSpinGemm(const B200Device &dev, float *d_C, int ldc, const TcOperand &A, const signed char *d_Q, int ldq, int m, TcWorkspace &ws);
+/* the same product from spins the caller keeps in bf16 ([roundUp(m,128)][A.Kp], padding zero), e.g. maintained by a flip kernel */
+void tcSpinGemmBf16(const B200Device &dev, float *d_C, int ldc, const TcOperand &A, const unsigned short *d_Qbf, int m);
+/* (re)build such a bf16 copy from int8 spins; allocates / zero-fills `qbf` when it is too small */
+void tcWidenSpins(const B200Device &dev, DevBuf<unsigned short> &qbf, const TcOperand &A, const signed char *d_Q, int ldq, int m);
 /* E_b = alpha (sum_i v_bi (g_i + sum_j A_ij u_bj) + f.u_b) + beta0 */
 void tcBatchedEnergy(const B200Device &dev, float *d_E, const TcOperand &A, const signed char *d_u, int ldu, const signed char *d_v, int ldv,
                      const float *d_g, const float *d_f, int nBatch, float alpha, float beta0, TcWorkspace &ws);

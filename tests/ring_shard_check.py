@@ -23,7 +23,8 @@ def main():
     from sqaod_b200.multigpu import RingShardedDenseAnnealer
     from oracle import pyoracle as orc
     sq.set_active_device(sq.Device(local))
-    cases = [(40, 2 * world, 4), (100, 6 * world, 3), (300, 20 * world, 2), (1000, 150 * world, 1), (2100, 8 * world, 1)]
+    cases = [(40, 2 * world, 4), (100, 6 * world, 3), (300, 20 * world, 2), (1000, 150 * world, 1), (2100, 8 * world, 1),
+             (64, 450 * world, 2), (36, 1001 * world, 1)]   # 3-4 and 6-7 trotters per CTA: the wide warp layout
     ok_all = True
     for N, m, steps in cases:
         for dtype in (np.float32, np.float64):

@@ -91,6 +91,10 @@ int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int d
 
 /* replica batch (no reference counterpart): R independent replicas of the problem, replica r seeded
  * seed + r, annealed side by side in one launch.  Spin and energy buffers then hold R x n_trotters rows, replica major. */
+/* a batch of n_problems DIFFERENT QUBOs of the same size (W: n_problems x N x N, row stride ldW elements) annealed side by side
+ * in one cooperative launch per step; problem r uses seed + r; spins / energies are returned as n_problems*m rows (SURVEY 8f-2:
+ * the caller loop of sqaodpy/sqaod/common/common.py:144-160 run for many problems at once) */
+int sqb_dg_annealer_set_qubo_batch(sqb_handle ann, const void *W, int n_problems, int N, int ldW, int optimize, int dtype);
 int sqb_dg_annealer_set_num_replicas(sqb_handle ann, int n_replicas, int dtype);
 int sqb_dg_annealer_get_num_replicas(sqb_handle ann, int *n_replicas, int dtype);
 

@@ -73,6 +73,8 @@ public:
     int numTrotters() const { return m_; }
     /* replica batch: R independent replicas of the problem (seed + r) annealed side by side; spin / energy rows are [r][y] */
     void setNumReplicas(int n);
+    void setQUBOBatch(const real *W, int nProblems, int N, int ldW, sq::OptimizeMethod om);
+    int numProblems() const { return nProblems_; }
     int numReplicas() const { return nReplicas_; }
     /* ring sharding over several GPUs: this solver anneals trotters [rank*m/world, (rank+1)*m/world) of one ring */
     void ringConfigure(int rank, int world, int mGlobal);
@@ -96,6 +98,8 @@ private:
     int ringRank_, ringWorld_, mRing_, yOff_;
     unsigned long long ringEpoch_;
     int nReplicas_, replicasPerLaunch_;
+    int nProblems_ = 1;            /* > 1: replica r anneals problem r (setQUBOBatch) */
+    std::vector<real> cBatch_;
     void allocHandoff();
     void freeHandoff();
     void closePeer(int side);

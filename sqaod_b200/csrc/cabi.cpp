@@ -210,6 +210,9 @@ int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, 
 int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getCounters(out8)) SQB_CATCH }
 int sqb_dg_annealer_get_spins(sqb_handle ann, signed char *q, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getSpinsRaw(q)) SQB_CATCH }
 
+int sqb_dg_annealer_set_qubo_batch(sqb_handle ann, const void *W, int n_problems, int N, int ldW, int optimize, int dtype) {
+    SQB_TRY DISPATCH(dtype, DGAX(real)->setQUBOBatch((const real *)W, n_problems, N, ldW, (sq::OptimizeMethod)optimize)) SQB_CATCH
+}
 int sqb_dg_annealer_set_num_replicas(sqb_handle ann, int n, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->setNumReplicas(n)) SQB_CATCH }
 int sqb_dg_annealer_get_num_replicas(sqb_handle ann, int *n, int dtype) { SQB_TRY DISPATCH(dtype, *n = DGAX(real)->numReplicas()) SQB_CATCH }
 int sqb_dg_annealer_ring_configure(sqb_handle ann, int rank, int world, int m_global, int dtype) {

@@ -72,6 +72,7 @@ template <class real> struct SweepParams {
     /* replica batch: blockIdx.y selects replica replicaBase + blockIdx.y (seed + replica, own spins and hand-off block) */
     int replicaBase;
     size_t qReplicaStride, handoffReplicaStride; /* in bytes */
+    size_t jReplicaStride, hReplicaStride;       /* in elements; 0: every replica anneals the same problem, else replica r has its own J and h */
     const signed char *haloQ[2];         /* spins of the left / right foreign neighbour at step start (pushed by the peers) */
     const unsigned long long *stepFlags; /* [2]: epoch of the last halo push received from the left / right peer */
     unsigned long long stepEpoch;
@@ -182,6 +183,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     const int replica = P.replicaBase + (int)blockIdx.y;
     const unsigned long long seedR = P.seed + (unsigned long long)replica;
     signed char *const qBase = P.q + (size_t)replica * P.qReplicaStride;
+    const real *const Jr = P.J + (size_t)replica * P.jReplicaStride;
+    const real *const hr = P.h + (size_t)replica * P.hReplicaStride;
     const size_t handoffOff = (size_t)replica * P.handoffReplicaStride / 8;
     unsigned long long *const aFlags = P.acceptFlags + handoffOff;
     unsigned long long *const sFlags = P.snapFlags + handoffOff;
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 xb[o] = ((2 * w64 + (bit >> 5)) << 5) | (bit & 31);
             }
             us[o] = negLogUniform<real>(p); /* accept iff dE*beta < -ln(u): no exp on the chain's critical path */
-            hs[o] = P.h[x];
+            hs[o] = hr[x];
         }
         if (remote) {
             for (int idx = t0; idx < 2 * Kw; idx += nthr) {
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         const int elems = min(CH, P.ldJ - ic * CH);
         const uint32_t bytes = (uint32_t)(elems * sizeof(real));
         mbarArriveExpectTx(&myBars[iStage], bytes);
-        tmaLoad1D(myRing + (size_t)iStage * CH, P.J + (size_t)ix * P.ldJ + (size_t)ic * CH, bytes, &myBars[iStage]);
+        tmaLoad1D(myRing + (size_t)iStage * CH, Jr + (size_t)ix * P.ldJ + (size_t)ic * CH, bytes, &myBars[iStage]);
         if (++iStage == S) iStage = 0;
         if (++ic == CPR) ic = 0;
     };
@@ -935,6 +938,7 @@ template <class real> void B200DenseGraphAnnealer<real>::setQUBO(const HostMatri
     sqb_throwErrorIf(!sq::isSymmetric(W), "%s, Matrix is not symmetric.", __func__);
     sqb_throwErrorIf(dev_ == NULL, "Device not set.");
     clearState(solProblemSet);
+    if (nProblems_ > 1) { nProblems_ = 1; nReplicas_ = 1; cBatch_.clear(); }
     N_ = W.rows;
     m_ = N_ / 4;
     om_ = om;
@@ -964,6 +968,41 @@ void B200DenseGraphAnnealer<real>::setHamiltonian(const HostVector &h, const Hos
     om_ = sq::optMinimize;
     c_ = c;
     uploadProblem(h.data, J.data, J.stride);
+    setState(solProblemSet);
+}
+
+/* A batch of DIFFERENT problems of the same size annealed side by side: problem r is replica r of the replica
+ * batch machinery, with its own J, h, c (and seed + r).  W: nProblems x N x N, row stride ldW elements. */
+template <class real> void B200DenseGraphAnnealer<real>::setQUBOBatch(const real *W, int nProblems, int N, int ldW, sq::OptimizeMethod om) {
+    sqb_throwErrorIf(nProblems < 1 || N < 1 || ldW < N, "%s: bad batch shape.", __func__);
+    sqb_throwErrorIf(dev_ == NULL, "Device not set.");
+    sqb_throwErrorIf(ringWorld_ > 1, "problem batches and ring sharding cannot be combined.");
+    for (int r = 0; r < nProblems; ++r) {
+        HostMatrix Wr(const_cast<real *>(W) + (size_t)r * N * ldW, N, N, ldW);
+        sqb_throwErrorIf(!sq::isSymmetric(Wr), "%s, matrix %d is not symmetric.", __func__, r);
+    }
+    clearState(solProblemSet);
+    N_ = N;
+    m_ = N_ / 4;
+    om_ = om;
+    nProblems_ = nProblems;
+    nReplicas_ = nProblems;
+    ldJ_ = sq::roundUp(N_, 128);
+    dJ_.alloc(dev_, (size_t)nProblems * N_ * ldJ_);
+    dh_.alloc(dev_, (size_t)nProblems * N_);
+    DevBuf<real> dW, dc;
+    dW.alloc(dev_, (size_t)N_ * ldJ_);
+    dc.alloc(dev_, nProblems);
+    for (int r = 0; r < nProblems; ++r) {
+        dev_->h2d2D(dW.p, sizeof(real) * ldJ_, W + (size_t)r * N * ldW, sizeof(real) * ldW, sizeof(real) * N_, N_);
+        devDenseHamiltonian<real>(*dev_, dh_.p + (size_t)r * N_, dJ_.p + (size_t)r * N_ * ldJ_, ldJ_, dc.p + r, dW.p, ldJ_, N_,
+                                  om == sq::optMaximize ? real(-1) : real(1));
+    }
+    tcJ_.ready = false; /* energies of a batch use the CUDA-core path, one problem at a time */
+    cBatch_.resize(nProblems);
+    dev_->d2h(cBatch_.data(), dc.p, sizeof(real) * nProblems);
+    dev_->synchronize();
+    c_ = cBatch_[0];
     setState(solProblemSet);
 }
 
@@ -1146,8 +1185,14 @@ template <class real> void B200DenseGraphAnnealer<real>::calculate_E() {
     /* E_y = -c - h.q_y - q_y^T J q_y, sign-flipped for maximize (CUDADenseGraphAnnealer.cu:260-272) */
     const real sign = (om_ == sq::optMaximize) ? real(-1) : real(1);
     bool done = false;
+    if (nProblems_ > 1) { /* problem batch: rows r*m .. r*m+m-1 belong to problem r */
+        for (int r = 0; r < nProblems_; ++r)
+            devBatchedEnergy<real>(*dev_, dE_.p + (size_t)r * m_, dJ_.p + (size_t)r * N_ * ldJ_, ldJ_, N_, N_, dq_.p + (size_t)r * m_ * ldq_, ldq_,
+                                   dq_.p + (size_t)r * m_ * ldq_, ldq_, dh_.p + (size_t)r * N_, NULL, m_, -sign, -sign * cBatch_[r]);
+        done = true;
+    }
     if constexpr (std::is_same<real, float>::value) {
-        if (tcJ_.ready && tcEnabled()) {
+        if (!done && tcJ_.ready && tcEnabled()) {
             tcBatchedEnergy(*dev_, dE_.p, tcJ_, dq_.p, ldq_, dq_.p, ldq_, dh_.p, NULL, m_ * nReplicas_, -sign, -sign * c_, tcWs_);
             done = true;
         }
@@ -1223,6 +1268,8 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
     P.snapBase = (launchCount_ + 1ull) * (unsigned long long)(nWindows_ + 2);
     P.stats = dStats_.p;
     P.qReplicaStride = (size_t)m_ * ldq_;
+    P.jReplicaStride = (nProblems_ > 1) ? (size_t)N_ * ldJ_ : 0;
+    P.hReplicaStride = (nProblems_ > 1) ? (size_t)N_ : 0;
     P.handoffReplicaStride = hl.total;
     void *args[] = {&P};
     const void *fn = sweepKernelFor<real>(sqa, K_);
@@ -1269,6 +1316,7 @@ template <class real> void B200DenseGraphAnnealer<real>::closePeer(int side) {
 }
 template <class real> void B200DenseGraphAnnealer<real>::setNumReplicas(int n) {
     sqb_throwErrorIf(n < 1, "number of replicas must be positive.");
+    sqb_throwErrorIf(nProblems_ > 1 && n != nProblems_, "a problem batch has one replica per problem (%d).", nProblems_);
     if (n != nReplicas_) clearState(solPrepared);
     nReplicas_ = n;
 }

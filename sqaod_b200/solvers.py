@@ -99,6 +99,18 @@ class DenseGraphAnnealer(_SolverBase):
         _lib.check(L.sqb_dg_annealer_set_qubo(self._cobj, ptr(W), W.shape[0], W.strides[0] // W.itemsize, int(optimize), self._dt))
         self._optimize = optimize
 
+    def set_qubo_batch(self, Ws, optimize=minimize):
+        """a batch of DIFFERENT problems of one size, annealed side by side in one launch per step (problem r uses seed + r).
+        Ws: array (n_problems, N, N) of symmetric matrices.  get_E / get_spins / get_q then return n_problems * n_trotters rows,
+        problem-major."""
+        Ws = np.ascontiguousarray(np.asarray(Ws, self.dtype))
+        if Ws.ndim != 3 or Ws.shape[1] != Ws.shape[2]:
+            raise ValueError('Ws must have shape (n_problems, N, N)')
+        for W in Ws:
+            common.check_dense_qubo(W)
+        _lib.check(L.sqb_dg_annealer_set_qubo_batch(self._cobj, ptr(Ws), Ws.shape[0], Ws.shape[1], Ws.shape[2], int(optimize), self._dt))
+        self._optimize = optimize
+
     def set_hamiltonian(self, h, J, c):
         common.check_dense_hJc(h, J, c)
         h, J = common.fix_type([h, J], self.dtype)

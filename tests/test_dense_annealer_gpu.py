@@ -191,3 +191,35 @@ def test_replica_batch_equals_separate_solvers(sq, N, m, R, algo, dtype):
         assert np.array_equal(one.get_spins(), qb[r]), 'replica %d differs' % r
         assert np.allclose(one.get_E(), Eb[r], rtol=tol(dtype), atol=tol(dtype) * 10)
     assert len(batch.get_q()) == R * m
+
+
+@pytest.mark.parametrize('dtype', DT)
+def test_problem_batch_equals_separate_solvers(sq, dtype):
+    """set_qubo_batch: R different problems in one launch per step; problem r must follow exactly the trajectory of a solver of
+    its own with seed + r."""
+    R, N, m, steps = 7, 72, 10, 3
+    Ws = np.stack([quantized_symmetric_W(N, 7000 + r, dtype) for r in range(R)])
+    batch = sq.dense_graph_annealer(None, sq.minimize, dtype, n_trotters=m)
+    batch.set_qubo_batch(Ws)
+    batch.set_preferences(n_trotters=m)
+    batch.seed(31); batch.prepare(); batch.randomize_spin()
+    singles = []
+    for r in range(R):
+        a = sq.dense_graph_annealer(Ws[r], sq.minimize, dtype, n_trotters=m)
+        a.seed(31 + r); a.prepare(); a.randomize_spin()
+        singles.append(a)
+    q = batch.get_spins()
+    assert q.shape == (R * m, N)
+    G, beta = 2.0, 3.0
+    for s in range(steps):
+        batch.anneal_one_step(G, beta)
+        for a in singles:
+            a.anneal_one_step(G, beta)
+        G *= 0.6
+        q = batch.get_spins()
+        for r, a in enumerate(singles):
+            assert np.array_equal(q[r * m:(r + 1) * m], a.get_spins()), 'problem %d, step %d' % (r, s)
+    E = batch.get_E()
+    for r, a in enumerate(singles):
+        assert np.allclose(E[r * m:(r + 1) * m], a.get_E(), rtol=tol(dtype), atol=tol(dtype) * 10)
+    assert len(np.unique(np.round(E, 3))) > R          # the problems really differ

@@ -78,8 +78,8 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def traffic_from_profile():
-    p = os.path.join(ROOT, 'profiles', 'dense_sweep_ncu_summary.json')
+def traffic_from_profile(mode):
+    p = os.path.join(ROOT, 'profiles', 'dense_sweep_ncu_summary.json' if mode == 'classic' else 'r1_field_sweep_ncu_summary.json')
     if os.path.exists(p):
         try:
             return json.load(open(p)).get('dram_bytes_per_launch')
@@ -141,6 +141,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--N', type=int, default=N_SPINS)
     ap.add_argument('--m', type=int, default=M_TROTTERS)
+    ap.add_argument('--sweep-mode', default='auto', choices=['auto', 'classic', 'field'],
+                    help="how the sweep gets its local fields: 'classic' streams one J row per attempt, 'field' keeps J.q in shared "
+                         "memory and streams one row per accepted flip (same Markov chain); 'auto' = the library's choice")
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -168,7 +171,9 @@ def main():
     W = make_problem(N)
     ann = sq.dense_graph_annealer(W, sq.minimize, np.float32, n_trotters=m, device=dev)
     ann.seed(1000 + rank)                       # independent replica per GPU
+    ann.set_sweep_mode(args.sweep_mode)
     ann.prepare()
+    mode = ann.get_sweep_mode()
     ann.randomize_spin()
 
     def barrier():
@@ -226,13 +231,15 @@ def main():
         algo_bytes = attempts_per_step * N * 4          # one J row per attempt
         achieved = algo_bytes / (ms / args.steps * 1e-3) / 1e9
         accepted = stats1['accepted'] - stats0['accepted']
-        traffic = traffic_from_profile() if (N == N_SPINS and m == M_TROTTERS) else None
+        traffic = traffic_from_profile(mode) if (N == N_SPINS and m == M_TROTTERS) else None
         line = {
             'metric': 'spin-flip attempts/sec (dense SQA N=8192 m=512)', 'value': value, 'unit': 'attempts/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'dense-graph SQA N=%d m=%d fp32 random QUBO (BASELINE.json configs[1]); one independent '
                                    'replica per GPU' % (N, m), 'G': G_FIXED, 'beta': BETA, 'algorithm': 'coloring',
+                       'sweep_mode': mode + (' (local fields J.q recomputed on the tensor cores every step, kept in shared memory, one J row '
+                                             'streamed per ACCEPTED flip)' if mode == 'field' else ' (one J row streamed per attempt)'),
                        'l2': 'J is %d MiB > 126 MB L2 and rows are drawn at random, no flush needed' % (N * N * 4 >> 20),
                        'acceptance_rate': accepted / float(attempts_per_step * args.steps),
                        'flag_waits': stats1['flag_waits'] - stats0['flag_waits'],
@@ -244,9 +251,11 @@ def main():
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
-                         'kernel': 'denseSweepKernel<float,true,16>', 'algorithmic_bytes_per_launch': algo_bytes,
+                         'kernel': 'denseSweepKernel<float,true,16,%s>' % ('true' if mode == 'field' else 'false'),
+                         'algorithmic_bytes_per_launch': algo_bytes,
                          # the part of the algorithmic bytes that really came from HBM (ncu dram bytes per launch, profiles/):
-                         # frac > 1 on the algorithmic figure is L2 reuse of J rows, not skipped work
+                         # frac > 1 on the algorithmic figure is L2 reuse of J rows (classic mode) or rows of rejected attempts
+                         # that were never needed (field mode: incremental local fields), not skipped work
                          'dram_GBps': (traffic / (ms / args.steps * 1e-3) / 1e9) if traffic else None,
                          'dram_frac': (traffic / (ms / args.steps * 1e-3) / 1e9 / peak) if traffic else None},
         }

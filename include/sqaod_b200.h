@@ -88,6 +88,14 @@ int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, 
  * [3] chain-warp busy cycles, [5] helper-warp busy cycles (snapshots, conflict masks), [6] prep-warp busy cycles (Philox
  * tables), [4] / [7] chain-warp cycles waiting for dot products / for neighbour data */
 int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int dtype);
+/* how annealOneStep obtains h_x + sum_j J_xj q_j (no reference counterpart; both modes run the same Markov chain):
+ *   0 "classic": one J row streamed per attempt (N*sizeof(real) bytes of traffic per attempt);
+ *   1 "field":   the local fields of every trotter are computed once per step (J.q spin GEMM, tensor cores for fp32), kept in
+ *                shared memory and updated with one J row per ACCEPTED flip;
+ *  -1 automatic (default): field mode whenever the field rows fit in shared memory.
+ * field_refresh > 0: number of steps between two recomputations of J.q (0: automatic).  Takes effect at the next prepare(). */
+int sqb_dg_annealer_set_sweep_mode(sqb_handle ann, int mode, int field_refresh, int dtype);
+int sqb_dg_annealer_get_sweep_mode(sqb_handle ann, int *mode, int dtype); /* the mode prepare() chose: 0 or 1 */
 
 /* replica batch (no reference counterpart): R independent replicas of the problem, replica r seeded
  * seed + r, annealed side by side in one launch.  Spin and energy buffers then hold R x n_trotters rows, replica major. */

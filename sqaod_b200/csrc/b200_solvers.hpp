@@ -23,6 +23,10 @@ template <class real>
 void devBipartiteEnergy2D(const B200Device &dev, real *d_E, int ldE, const real *d_b0, const real *d_b1, const real *d_W, int ldW,
                           int N0, int N1, const signed char *d_x0, int ldx0, int n0, const signed char *d_x1, int ldx1, int n1);
 
+/* C[y][i] = sum_k Q[y][k] A[i][k] on CUDA cores (bipartite_annealer.cu) */
+template <class real>
+void devSpinGemm(const B200Device &dev, real *C, int ldc, const real *A, int ldA, const signed char *Q, int ldq, int m, int NA, int NF);
+
 void launchRandomizeSpin(const B200Device &dev, signed char *q, int ldq, int N, int m, unsigned long long seed,
                          unsigned long long count, unsigned domain, int yOff = 0, int mPerReplica = 0);
 long long ringSpinDot(const B200Device &dev, const signed char *q, int ldq, int N, int m);
@@ -110,6 +114,19 @@ private:
     unsigned long long seed_, step_, randomizeCount_, launchCount_;
     int grid_, chunkElems_, chunksPerRow_, stages_, nw64_, nWindows_, K_;
     int dotWarps_ = 12;
+    /* field mode of the sweep (dense_annealer.cu): local fields J.q kept in shared memory and updated per accepted flip */
+    bool fieldMode_ = false;
+    DevBuf<real> dF_;              /* [m * replicas][ldJ] fields at step start */
+    bool fieldsValid_ = false;     /* dF_ matches dq_ (cleared by everything that writes spins or the problem) */
+    int fieldRefresh_ = 1, stepsSinceRefresh_ = 0; /* recompute F = J.q with the spin GEMM every fieldRefresh_ steps */
+    int sweepModeWanted_ = -1, fieldRefreshWanted_ = 0; /* setSweepMode(); -1 / 0: automatic */
+    void refreshFields();
+public:
+    bool fieldMode() const { return fieldMode_; }
+    /* mode -1: automatic (field mode whenever the field rows fit in shared memory), 0: classic (one J row per attempt),
+     * 1: field mode (error in prepare() when it does not fit); fieldRefresh > 0: steps between two J.q recomputations */
+    void setSweepMode(int mode, int fieldRefresh);
+private:
     size_t smemBytes_;
     mutable unsigned long long lastBarrierWaitDot_ = 0, lastBarrierWaitChain_ = 0;
     HostVector E_;

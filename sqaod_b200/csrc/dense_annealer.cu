@@ -78,14 +78,20 @@ template <class real> struct SweepParams {
     unsigned long long stepEpoch;
     unsigned long long *peerFlags[2], *peerSnapFlags[2], *peerSnapBits[2]; /* the peers' arrays (NVLink P2P), or NULL */
     unsigned long long roundBase, snapBase;
+    /* field mode (FIELD kernels): local fields F[y][j] = sum_i J[j][i] q[y][i] of every trotter, [rows][ldF] in global memory at
+     * step start (spin GEMM or the previous step's write-back); kept in shared memory and updated incrementally by the sweep */
+    real *F;
+    int ldF, writeBackF;
     unsigned long long *stats;       /* [0] accepted flips, [1] remote wait polls, [2]/[3] busy cycles of dot warp 0 / the chain warp, summed over CTAs */
 };
 
 /* shared-memory carve-up, identical on host and device */
 template <class real> struct SweepSmem {
-    size_t ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, confAny, accLog, counter, total;
-    __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K, int dotWarps) {
+    size_t field, ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, confAny, accLog, sgnLog, counter, total;
+    /* fieldElems > 0: field mode -- T rows of fieldElems local fields instead of the TMA ring (stages == 0) */
+    __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K, int dotWarps, int fieldElems = 0) {
         size_t o = 0;
+        field = o; o += (size_t)T * fieldElems * sizeof(real);
         ring = o; o += (size_t)dotWarps * stages * chunkElems * sizeof(real);
         bars = o; o += (size_t)dotWarps * stages * 8;
         qcur = o; o += (size_t)T * nw64 * 8;
@@ -103,6 +109,7 @@ template <class real> struct SweepSmem {
         conf = o; o += (size_t)2 * 2 * K * 4;
         confAny = o; o += 16;
         accLog = o; o += (size_t)2 * T * 4;
+        sgnLog = o; o += (size_t)2 * T * 4;
         o = (o + 15) & ~(size_t)15;
         counter = o; o += 32;
         total = (o + 127) & ~(size_t)127;
@@ -171,12 +178,35 @@ __device__ __forceinline__ void accumGroup(const double *buf, uint32_t nib, Acc4
     a.a3 += signFlip(v1.y, neg << 28);
 }
 
+/* field mode: F[0..3] += c * J[0..3] (c = +-2, so the products are exact); 4 consecutive elements per lane */
+struct RowVec4f { float4 v; };
+struct RowVec4d { double2 v0, v1; };
+template <class real> struct RowVec4;
+template <> struct RowVec4<float> { typedef RowVec4f type; };
+template <> struct RowVec4<double> { typedef RowVec4d type; };
+__device__ __forceinline__ void loadRow4(const float *p, RowVec4f &r) { r.v = __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void loadRow4(const double *p, RowVec4d &r) {
+    r.v0 = __ldg(reinterpret_cast<const double2 *>(p));
+    r.v1 = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+}
+__device__ __forceinline__ void axpyRow4(float *F, float c, const RowVec4f &r) {
+    float4 f = *reinterpret_cast<float4 *>(F);
+    f.x = fmaf(c, r.v.x, f.x); f.y = fmaf(c, r.v.y, f.y); f.z = fmaf(c, r.v.z, f.z); f.w = fmaf(c, r.v.w, f.w);
+    *reinterpret_cast<float4 *>(F) = f;
+}
+__device__ __forceinline__ void axpyRow4(double *F, double c, const RowVec4d &r) {
+    double2 f0 = *reinterpret_cast<double2 *>(F), f1 = *(reinterpret_cast<double2 *>(F) + 1);
+    f0.x = fma(c, r.v0.x, f0.x); f0.y = fma(c, r.v0.y, f0.y); f1.x = fma(c, r.v1.x, f1.x); f1.y = fma(c, r.v1.y, f1.y);
+    *reinterpret_cast<double2 *>(F) = f0;
+    *(reinterpret_cast<double2 *>(F) + 1) = f1;
+}
+
 __device__ __forceinline__ int sweepPhase(int y, int m) { /* 0: even, 1: trotter m-1 of an odd ring, 2: odd */
     if (y & 1) return 2;
     return ((m & 1) && y == m - 1) ? 1 : 0;
 }
 
-template <class real, bool SQA, int K>
+template <class real, bool SQA, int K, bool FIELD>
 __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepParams<real> P) {
     extern __shared__ __align__(128) unsigned char smem[];
     /* independent replicas of the same problem share J and h; seed, spins and hand-off block are per replica */
@@ -209,7 +239,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     const int CH = P.chunkElems, CPR = P.chunksPerRow, S = P.stages, NW = P.nw64;
     const int GPC = CH >> 7;
 
-    const SweepSmem<real> L(maxT, NW, CH, S, K, P.dotWarps);
+    const SweepSmem<real> L(maxT, NW, CH, S, K, P.dotWarps, FIELD ? P.ldF : 0);
+    real *field = reinterpret_cast<real *>(smem + L.field);  /* FIELD: [maxT][ldF] local fields sum_i J[j][i] q[t][i] */
     real *ring = reinterpret_cast<real *>(smem + L.ring);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
     unsigned long long *qcur = reinterpret_cast<unsigned long long *>(smem + L.qcur);
@@ -225,6 +256,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     uint32_t *conf = reinterpret_cast<uint32_t *>(smem + L.conf);       /* [2 buffers][2 sides][K] */
     uint32_t *confAny = reinterpret_cast<uint32_t *>(smem + L.confAny); /* [2 buffers][2 sides]: rounds with a non-empty mask */
     uint32_t *accLog = reinterpret_cast<uint32_t *>(smem + L.accLog);   /* [2 buffers][maxT]: accept bits of a window */
+    uint32_t *sgnLog = reinterpret_cast<uint32_t *>(smem + L.sgnLog);   /* [2 buffers][maxT]: spin (1 = up) before each attempt of a window */
     unsigned int *taskCounter = reinterpret_cast<unsigned int *>(smem + L.counter);
 
     /* ring topology: local index l <-> global trotter (yOff + l) mod mRing */
@@ -363,6 +395,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     prepWindow(0, tid, SW_THREADS);
     prepWindow(1, tid, SW_THREADS);
     prepWindow(2, tid, SW_THREADS);
+    real *const Fg = FIELD ? P.F + ((size_t)replica * m + y0) * P.ldF : NULL; /* this CTA's rows of the field matrix */
+    if (FIELD) { /* ldF is a multiple of 128 elements: 16-byte copies */
+        const int n16 = (int)((size_t)T * P.ldF * sizeof(real) / 16);
+        const int4 *src = reinterpret_cast<const int4 *>(Fg);
+        int4 *dst = reinterpret_cast<int4 *>(field);
+        for (int i = tid; i < n16; i += SW_THREADS) dst[i] = __ldcg(src + i);
+    }
     __syncthreads();
     for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
     for (int i = tid; i < 2 * NW; i += SW_THREADS) nbsnap[2 * NW + i] = nbsnap[i]; /* windows 0 and 1 both start from S_0 */
@@ -535,6 +574,100 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         }
     };
 
+    /* ---------------- field mode: what the dot warps do instead of streaming one J row per attempt ----------------
+     * The local fields F[t][j] = sum_i J[j][i] q_t[i] of the owned trotters live in shared memory.  Dot warp d owns the
+     * 128-column groups g = d (mod #dot warps) of every row.  For chain window w it
+     *   1. gathers the <= 2K-1 cross terms J[x][x'] of every attempt straight from global memory (4-byte gathers),
+     *   2. folds the flips ACCEPTED in window w-2 into its columns: F[t][.] -= 2 q_old J[x][.] (J symmetric) -- the only
+     *      full-row traffic left, acceptance-rate x one row per attempt,
+     *   3. hands the chain scaleA (h[x] + 2 F[t][x]) for the attempts of window w whose column it owns.
+     * F then holds exactly the flips of windows <= w-2, i.e. it is the sum against the snapshot S_{w-1} the classic kernel
+     * reduces rows against, so the chain (fold of window w-1, repair with the window's own flips) is unchanged. */
+    const int nDot = P.dotWarps;
+    const int nGroups = FIELD ? (P.ldF >> 7) : 0;
+    auto applyFlips = [&](int wf) {
+        const int wb = wf & 1, ws = wf & (SW_TAB_SLOTS - 1);
+        for (int t = 0; t < T; ++t) {
+            uint32_t bits = accLog[wb * maxT + t];
+            const uint32_t sg = sgnLog[wb * maxT + t];
+            real *Frow = field + (size_t)t * P.ldF + lane * 4;
+            while (bits) {
+                const int rl = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int x = xs[(ws * maxT + t) * K + rl];
+                const real c = ((sg >> rl) & 1u) ? real(-2) : real(2); /* q_old = +1: the sum loses 2 J */
+                const real *Jrow = Jr + (size_t)x * P.ldJ + lane * 4;
+                for (int g0 = dw; g0 < nGroups; g0 += nDot * 8) {
+                    typename RowVec4<real>::type v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int g = g0 + u * nDot;
+                        if (g < nGroups) loadRow4(Jrow + (size_t)g * 128, v[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int g = g0 + u * nDot;
+                        if (g < nGroups) axpyRow4(Frow + (size_t)g * 128, c, v[u]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    };
+    auto crossLoad = [&](int w, int e) -> real { /* lane j < K: J[x][x of round j of window w-1]; K <= j < 2K: round j-K of w */
+        const int slot = w & (SW_TAB_SLOTS - 1);
+        const int t = e % T, rl = e / T;
+        int px = -1;
+        if (lane < K) { if (w > 0) px = xs[(((w - 1) & (SW_TAB_SLOTS - 1)) * maxT + t) * K + lane]; }
+        else if (lane < 2 * K && lane - K < rl) px = xs[(slot * maxT + t) * K + (lane - K)];
+        if (px < 0) return real(0);
+        const int x = xs[(slot * maxT + t) * K + rl];
+        return __ldg(Jr + (size_t)x * P.ldJ + px);
+    };
+    auto fieldWindow = [&](int w) {
+        const int Kw = roundsIn(w), buf = w & 1, slot = w & (SW_TAB_SLOTS - 1);
+        const int nEnt = T * Kw;
+        uint32_t handled = 0;
+        real cv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { /* first batch of gathers in flight while the rows of the accepted flips stream */
+            const int e = dw + u * nDot;
+            cv[u] = (e < nEnt) ? crossLoad(w, e) : real(0);
+        }
+        if (w >= 2) applyFlips(w - 2);
+        for (int e0 = dw;;) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * nDot;
+                if (e < nEnt) {
+                    const int t = e % T, rl = e / T;
+                    if (lane < 2 * K) cross[((buf * maxT + t) * K + rl) * (2 * K) + lane] = cv[u];
+                    ++handled;
+                }
+            }
+            e0 += 4 * nDot;
+            if (e0 >= nEnt) break;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * nDot;
+                cv[u] = (e < nEnt) ? crossLoad(w, e) : real(0);
+            }
+        }
+        uint32_t mine = 0;
+        for (int e = lane; e < nEnt; e += 32) {
+            const int t = e % T, rl = e / T;
+            const int o = (slot * maxT + t) * K + rl;
+            const int x = xs[o];
+            if ((x >> 7) % nDot == dw) {
+                dots[(buf * maxT + t) * K + rl] = P.scaleA * (hs[o] + real(2) * field[(size_t)t * P.ldF + x]);
+                ++mine;
+            }
+        }
+        handled += __reduce_add_sync(0xffffffffu, mine);
+        __syncwarp(); /* every lane's dots / cross stores before lane 0's release */
+        if (lane == 0 && handled) redAddReleaseCta(aRowsDone + 4u * (uint32_t)buf, handled); /* the chain expects 2 per attempt */
+    };
+
     if (tid == 0) {
         stReleaseCta(aRowsDone, 0u); stReleaseCta(aRowsDone + 4, 0u); stReleaseCta(aReplayDone, 0u);
         stReleaseCta(aSnapCount, 1u); stReleaseCta(aNbCount, 1u); stReleaseCta(aPrepCount, 3u);
@@ -546,7 +679,28 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
      * HBM, bandwidth is shared in proportion to the bytes each SM has outstanding, and all CTAs should finish a window at
      * the same time (512 trotters on 148 SMs: 4 or 3 per CTA -> 12 or 9 streaming warps). */
     const int activeDotWarps = max(1, (P.dotWarps * T + maxT - 1) / maxT);
-    if (dotWarp && dw < activeDotWarps) {
+    if (FIELD && dotWarp) {
+        for (int w = 0; w < nW; ++w) {
+            waitCount(aPrepCount, (uint32_t)w + 1u, 20);                 /* tables of window w (and w-1) */
+            if (w >= 2) waitCount(aReplayDone, (uint32_t)w - 1u, 20);    /* window w-2 replayed: its flips are logged, its buffers free */
+            fieldWindow(w);
+        }
+        if (P.writeBackF) { /* the last two windows' flips, so that F matches the final spins; then back to global memory */
+            for (int wf = max(nW - 2, 0); wf < nW; ++wf) {
+                waitCount(aReplayDone, (uint32_t)wf + 1u, 20);
+                applyFlips(wf);
+            }
+            for (int t = 0; t < T; ++t)
+                for (int g = dw; g < nGroups; g += nDot) {
+                    const size_t o = (size_t)t * P.ldF + (size_t)g * 128 + lane * 4;
+                    if (sizeof(real) == 4) *reinterpret_cast<int4 *>(Fg + o) = *reinterpret_cast<const int4 *>(field + o);
+                    else {
+                        *reinterpret_cast<int4 *>(Fg + o) = *reinterpret_cast<const int4 *>(field + o);
+                        *(reinterpret_cast<int4 *>(Fg + o) + 1) = *(reinterpret_cast<const int4 *>(field + o) + 1);
+                    }
+                }
+        }
+    } else if (!FIELD && dotWarp && dw < activeDotWarps) {
         if (lane == 0)
             for (int s = 0; s < S; ++s) issueNext();
         int curW = -1;
@@ -573,6 +727,15 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         for (int w = 1; w < nW; ++w) {
             waitCount(aReplayDone, (uint32_t)w, 20);
             snapshotWindow(w);
+            if (FIELD) { /* the dot warps read window w-2's table slot until window w's fields are out: neighbour data first */
+                if (w + 1 < nW) { neighbourWindow(w + 1); signalCount(aNbCount, (uint32_t)w + 2u); }
+                if (w + 2 < nW) {
+                    waitCount(aRowsDone + 4u * (uint32_t)(w & 1), 2u * (uint32_t)((w >> 1) * TPW + roundsIn(w) * T), 20);
+                    prepWindow(w + 2, lane, 32);
+                    signalCount(aPrepCount, (uint32_t)w + 3u);
+                }
+                continue;
+            }
             if (w + 2 < nW) { prepWindow(w + 2, lane, 32); signalCount(aPrepCount, (uint32_t)w + 3u); }
             if (w + 1 < nW) { neighbourWindow(w + 1); signalCount(aNbCount, (uint32_t)w + 2u); }
         }
@@ -588,6 +751,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         /* tables of window wp go to the slot of window wp-4, dead once S_{wp-2} is built (window wp-3 replayed) */
         for (int wp = 3; wp < nW; ++wp) {
             waitCount(aSnapCount, (uint32_t)wp - 1u, 20);
+            if (FIELD) /* the dot warps read the slot of window wp-4 (its accepted flips) until the fields of window wp-2 are out */
+                waitCount(aRowsDone + 4u * (uint32_t)(wp & 1), 2u * (uint32_t)(((wp - 2) >> 1) * TPW + roundsIn(wp - 2) * T), 20);
             prepWindow(wp, lane, 32);
             signalCount(aPrepCount, (uint32_t)wp + 1u);
         }
@@ -622,7 +787,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             const unsigned long long *nbRows = nbsnap + (size_t)buf * 2 * NW;
             const uint32_t *confW = conf + buf * 2 * K;
             /* every row of this window reduced (and, through it, the window's tables in place); neighbour data in place */
-            waitCount(aRowsDone + 4u * (uint32_t)buf, (uint32_t)((w >> 1) * TPW + Kw * T), 0);
+            waitCount(aRowsDone + 4u * (uint32_t)buf, (FIELD ? 2u : 1u) * (uint32_t)((w >> 1) * TPW + Kw * T), 0);
             const long long waitedRows = waited;
             if (remote) waitCount(aNbCount, (uint32_t)w + 1u, 0);
             waitedNb += waited - waitedRows;
@@ -757,7 +922,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 core(2);
                 if (++fs == SW_FLAG_RING) fs = 0;
             }
-            if (active) accLog[buf * maxT + lane] = accC;
+            if (active) {
+                accLog[buf * maxT + lane] = accC;
+                if (FIELD) sgnLog[buf * maxT + lane] = sgnC;
+            }
             nAccepted += (unsigned long long)__popc(accC);
             accP = accC; sgnP = sgnC;
             signalCount(aReplayDone, (uint32_t)w + 1u);
@@ -864,12 +1032,15 @@ struct HandoffLayout { /* one block per solver so that a single IPC handle expos
     }
 };
 
-template <class real> static const void *sweepKernelFor(bool sqa, int K) {
+template <class real, bool FIELD> static const void *sweepKernelForMode(bool sqa, int K) {
     switch (K) {
-    case 16: return sqa ? (const void *)denseSweepKernel<real, true, 16> : (const void *)denseSweepKernel<real, false, 16>;
-    case 8: return sqa ? (const void *)denseSweepKernel<real, true, 8> : (const void *)denseSweepKernel<real, false, 8>;
-    default: return sqa ? (const void *)denseSweepKernel<real, true, 4> : (const void *)denseSweepKernel<real, false, 4>;
+    case 16: return sqa ? (const void *)denseSweepKernel<real, true, 16, FIELD> : (const void *)denseSweepKernel<real, false, 16, FIELD>;
+    case 8: return sqa ? (const void *)denseSweepKernel<real, true, 8, FIELD> : (const void *)denseSweepKernel<real, false, 8, FIELD>;
+    default: return sqa ? (const void *)denseSweepKernel<real, true, 4, FIELD> : (const void *)denseSweepKernel<real, false, 4, FIELD>;
     }
+}
+template <class real> static const void *sweepKernelFor(bool sqa, int K, bool field) {
+    return field ? sweepKernelForMode<real, true>(sqa, K) : sweepKernelForMode<real, false>(sqa, K);
 }
 
 /* =====================================================================================
@@ -938,6 +1109,7 @@ template <class real> void B200DenseGraphAnnealer<real>::setQUBO(const HostMatri
     sqb_throwErrorIf(!sq::isSymmetric(W), "%s, Matrix is not symmetric.", __func__);
     sqb_throwErrorIf(dev_ == NULL, "Device not set.");
     clearState(solProblemSet);
+    fieldsValid_ = false;
     if (nProblems_ > 1) { nProblems_ = 1; nReplicas_ = 1; cBatch_.clear(); }
     N_ = W.rows;
     m_ = N_ / 4;
@@ -963,6 +1135,7 @@ void B200DenseGraphAnnealer<real>::setHamiltonian(const HostVector &h, const Hos
     sqb_throwErrorIf(!sq::isSymmetric(J), "%s, Matrix is not symmetric.", __func__);
     sqb_throwErrorIf(dev_ == NULL, "Device not set.");
     clearState(solProblemSet);
+    fieldsValid_ = false;
     N_ = J.rows;
     m_ = N_ / 4;
     om_ = sq::optMinimize;
@@ -982,6 +1155,7 @@ template <class real> void B200DenseGraphAnnealer<real>::setQUBOBatch(const real
         sqb_throwErrorIf(!sq::isSymmetric(Wr), "%s, matrix %d is not symmetric.", __func__, r);
     }
     clearState(solProblemSet);
+    fieldsValid_ = false;
     N_ = N;
     m_ = N_ / 4;
     om_ = om;
@@ -1074,6 +1248,22 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
                 }
             }
         }
+        /* Field mode: no TMA ring, T rows of local fields instead.  Chosen whenever the rows fit next to the tables (the
+         * traffic is acceptance-rate x one J row per attempt instead of one row per attempt); SQAOD_B200_SWEEP_FIELD=0/1
+         * overrides.  Not combined with ring sharding or problem batches. */
+        fieldMode_ = false;
+        const char *fe = getenv("SQAOD_B200_SWEEP_FIELD");
+        const bool fieldWanted = (sweepModeWanted_ >= 0) ? sweepModeWanted_ != 0 : (fe ? atoi(fe) != 0 : true);
+        sqb_throwErrorIf(sweepModeWanted_ == 1 && (ringWorld_ > 1 || nProblems_ > 1), "field mode cannot be combined with ring sharding or problem batches.");
+        if (fieldWanted && ringWorld_ <= 1 && nProblems_ <= 1) {
+            for (int k = SW_MAX_K; k >= 4; k >>= 1) {
+                if (forceK ? (k != forceK) : (k > 4 && (size_t)2 * maxT * k * 2 * k * sizeof(real) > (size_t)48 * 1024)) continue;
+                if (SweepSmem<real>(maxT, nw64, 128, 0, k, dotWarps_, ldJ_).total > dev_->smemPerBlockOptin()) continue;
+                fieldMode_ = true; K = k; chunkElems = 128; stages = 0;
+                break;
+            }
+        }
+        sqb_throwErrorIf(sweepModeWanted_ == 1 && !fieldMode_, "field mode: %d trotters per CTA x %d fields do not fit in shared memory.", maxT, (int)ldJ_);
         sqb_throwErrorIf(K == 0, "problem too large for the sweep kernel's shared memory (N=%d, m=%d).", N_, m_);
     }
     K_ = K;
@@ -1082,13 +1272,25 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     chunksPerRow_ = (ldJ_ + chunkElems - 1) / chunkElems;
     stages_ = stages;
     nw64_ = nw64;
-    smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages, K, dotWarps_).total;
+    smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages, K, dotWarps_, fieldMode_ ? ldJ_ : 0).total;
     nWindows_ = (N_ + K - 1) / K;
+    fieldsValid_ = false;
+    if (fieldMode_) {
+        dF_.alloc(dev_, (size_t)rows * ldJ_);
+        dev_->makeCurrent();
+        CUDA_CHECK(cudaMemsetAsync(dF_.p, 0, sizeof(real) * (size_t)rows * ldJ_, dev_->stream()));
+        /* the tcgen05 GEMM costs ~1 % of a step: refresh every step; the CUDA-core GEMM (fp64) only now and then */
+        bool tc = false;
+        if constexpr (std::is_same<real, float>::value) tc = tcJ_.ready && tcEnabled();
+        fieldRefresh_ = tc ? 1 : 16;
+        if (getenv("SQAOD_B200_FIELD_REFRESH")) fieldRefresh_ = std::max(1, atoi(getenv("SQAOD_B200_FIELD_REFRESH")));
+        if (fieldRefreshWanted_ > 0) fieldRefresh_ = fieldRefreshWanted_;
+    }
     allocHandoff();
     dStats_.alloc(dev_, 8);
     launchCount_ = 0;
-    CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(true, K_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
-    CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(false, K_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
+    CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(true, K_, fieldMode_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
+    CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(false, K_, fieldMode_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
     xlist_.clear();
     qlist_.clear();
     setState(solPrepared);
@@ -1098,6 +1300,7 @@ template <class real> void B200DenseGraphAnnealer<real>::randomizeSpin() {
     throwErrorIfNotPrepared();
     launchRandomizeSpin(*dev_, dq_.p, ldq_, N_, m_ * nReplicas_, seed_, randomizeCount_++, DOM_RANDOMIZE, ringWorld_ > 1 ? yOff_ : 0,
                         nReplicas_ > 1 ? m_ : 0);
+    fieldsValid_ = false;
     setState(solQSet);
 }
 
@@ -1112,6 +1315,7 @@ template <class real> void B200DenseGraphAnnealer<real>::set_q(const sq::BitSet 
     CUDA_CHECK(cudaGetLastError());
     ++dev_->launchCount;
     dev_->synchronize();
+    fieldsValid_ = false;
     setState(solQSet);
 }
 
@@ -1129,6 +1333,7 @@ template <class real> void B200DenseGraphAnnealer<real>::set_qset(const sq::BitS
     for (int y = 0; y < m_ * nReplicas_; ++y) memcpy(&hq_[(size_t)y * ldq_], q[y].data, N_);
     dev_->h2d(dq_.p, hq_.data(), hq_.size());
     dev_->synchronize();
+    fieldsValid_ = false;
     setState(solQSet);
 }
 
@@ -1141,6 +1346,7 @@ template <class real> void B200DenseGraphAnnealer<real>::setSpinsRaw(const signe
     } else if (m != m_ || !isPrepared()) { m_ = m; prepare(); }
     dev_->h2d2D(dq_.p, ldq_, q, N_, N_, m_ * nReplicas_);
     dev_->synchronize();
+    fieldsValid_ = false;
     setState(solQSet);
 }
 
@@ -1267,12 +1473,20 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
     P.roundBase = (launchCount_ + 1ull) * (unsigned long long)(N_ + SW_FLAG_RING);
     P.snapBase = (launchCount_ + 1ull) * (unsigned long long)(nWindows_ + 2);
     P.stats = dStats_.p;
+    P.F = NULL; P.ldF = 0; P.writeBackF = 0;
+    if (fieldMode_) {
+        if (!fieldsValid_ || stepsSinceRefresh_ >= fieldRefresh_) refreshFields();
+        ++stepsSinceRefresh_;
+        P.F = dF_.p; P.ldF = ldJ_;
+        P.writeBackF = (fieldRefresh_ > 1) ? 1 : 0; /* refreshed before every step otherwise */
+        fieldsValid_ = (P.writeBackF != 0);
+    }
     P.qReplicaStride = (size_t)m_ * ldq_;
     P.jReplicaStride = (nProblems_ > 1) ? (size_t)N_ * ldJ_ : 0;
     P.hReplicaStride = (nProblems_ > 1) ? (size_t)N_ : 0;
     P.handoffReplicaStride = hl.total;
     void *args[] = {&P};
-    const void *fn = sweepKernelFor<real>(sqa, K_);
+    const void *fn = sweepKernelFor<real>(sqa, K_, fieldMode_);
     dev_->makeCurrent();
     for (int base = 0; base < nReplicas_; base += replicasPerLaunch_) {
         P.replicaBase = base;
@@ -1283,6 +1497,29 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
     ++launchCount_;
     ++step_;
     if (ringWorld_ > 1) ringPushHalos(); /* per-sweep boundary exchange over NVLink */
+}
+
+/* F[y][j] = sum_i J[j][i] q[y][i] for every trotter (and replica): the local-field contraction of the north star, on the
+ * tcgen05 split-bf16 GEMM for fp32 (energy_tc.cu), on the CUDA-core spin GEMM otherwise */
+template <class real> void B200DenseGraphAnnealer<real>::setSweepMode(int mode, int fieldRefresh) {
+    sqb_throwErrorIf(mode < -1 || mode > 1, "sweep mode must be -1 (automatic), 0 (classic) or 1 (field).");
+    sweepModeWanted_ = mode;
+    fieldRefreshWanted_ = std::max(0, fieldRefresh);
+    clearState(solPrepared);
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::refreshFields() {
+    const int rows = m_ * nReplicas_;
+    bool done = false;
+    if constexpr (std::is_same<real, float>::value) {
+        if (tcJ_.ready && tcEnabled()) {
+            tcSpinGemm(*dev_, dF_.p, ldJ_, tcJ_, dq_.p, ldq_, rows, tcWs_);
+            done = true;
+        }
+    }
+    if (!done) devSpinGemm<real>(*dev_, dF_.p, ldJ_, dJ_.p, ldJ_, dq_.p, ldq_, rows, N_, N_);
+    fieldsValid_ = true;
+    stepsSinceRefresh_ = 0;
 }
 
 /* ---------------- ring sharding over several GPUs ---------------- */

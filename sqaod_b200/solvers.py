@@ -210,6 +210,16 @@ class DenseGraphAnnealer(_SolverBase):
     def ring_push_halos(self):
         _lib.check(L.sqb_dg_annealer_ring_push_halos(self._cobj, self._dt))
 
+    def set_sweep_mode(self, mode='auto', field_refresh=0):
+        """'classic': one J row per attempt; 'field': local fields in shared memory, one J row per accepted flip; 'auto'."""
+        code = {'auto': -1, 'classic': 0, 'field': 1}[mode]
+        _lib.check(L.sqb_dg_annealer_set_sweep_mode(self._cobj, code, int(field_refresh), self._dt))
+
+    def get_sweep_mode(self):
+        v = C.c_int(0)
+        _lib.check(L.sqb_dg_annealer_get_sweep_mode(self._cobj, C.byref(v), self._dt))
+        return 'field' if v.value else 'classic'
+
     def get_stats(self):
         a = C.c_ulonglong(0); w = C.c_ulonglong(0)
         _lib.check(L.sqb_dg_annealer_get_stats(self._cobj, C.byref(a), C.byref(w), self._dt))

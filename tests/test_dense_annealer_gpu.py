@@ -103,16 +103,29 @@ CHAIN_CASES = [
 ]
 
 
+def field_mode_fits(N, m, dtype):
+    """mirror of prepare()'s plan: T rows of roundUp(N,128) fields next to ~40 KB of tables in 227 KB of shared memory"""
+    T = -(-m // min(148, m))
+    return T * (-(-N // 128) * 128) * np.dtype(dtype).itemsize <= 180 * 1024
+
+
 @pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('mode', ['classic', 'field', 'field_writeback'])
 @pytest.mark.parametrize('N,m,algo,steps', CHAIN_CASES)
-def test_exact_chain_vs_oracle(sq, oracle, N, m, algo, steps, dtype):
-    """The kernel and the oracle (philox mode) must produce identical spins step by step."""
+def test_exact_chain_vs_oracle(sq, oracle, N, m, algo, steps, dtype, mode):
+    """The kernel and the oracle (philox mode) must produce identical spins step by step -- in both sweep modes: 'classic'
+    (one J row per attempt), 'field' (local fields from the spin GEMM at step start, updated per accepted flip) and
+    'field_writeback' (fields carried from step to step in global memory, recomputed only every 1000 steps)."""
+    if mode != 'classic' and not field_mode_fits(N, m, dtype):
+        pytest.skip('field rows do not fit in shared memory for this shape')
     W = quantized_symmetric_W(N, 1000 + N, dtype)
     for seed in range(5, 25):
         ref = oracle.DenseGraphAnnealer(W, 0, dtype, n_trotters=m, algorithm=algo, rng='philox')
         ref.seed(seed); ref.prepare(); ref.randomize_spin()
         ann = sq.dense_graph_annealer(W, sq.minimize, dtype, n_trotters=m, algorithm=algo)
+        ann.set_sweep_mode('classic' if mode == 'classic' else 'field', 1000 if mode == 'field_writeback' else 0)
         ann.seed(seed); ann.prepare(); ann.randomize_spin()
+        assert ann.get_sweep_mode() == ('classic' if mode == 'classic' else 'field')
         assert np.array_equal(ann.get_spins(), ref.get_q()), 'randomize_spin stream differs'
         G, beta = (3.0, 1. / 0.3) if algo == 'coloring' else (2.0, 1.0)
         traj_ok = True
@@ -223,3 +236,63 @@ def test_problem_batch_equals_separate_solvers(sq, dtype):
     for r, a in enumerate(singles):
         assert np.allclose(E[r * m:(r + 1) * m], a.get_E(), rtol=tol(dtype), atol=tol(dtype) * 10)
     assert len(np.unique(np.round(E, 3))) > R          # the problems really differ
+
+
+FIELD_CASES = [
+    # N, m, algorithm, steps, G0   (shapes where rows are long enough that the field update spans many column groups)
+    (1500, 9, 'coloring', 3, 3.0),      # 12 column groups over 12 dot warps, odd ring
+    (3000, 40, 'coloring', 2, 2.0),     # two super-blocks, several groups per warp
+    (8192, 8, 'coloring', 1, 1.0),      # the C2 row length
+    (2048, 300, 'coloring', 1, 0.5),    # 3 / 2 trotters per CTA: wide layout next to the chain-critical one
+    (700, 5, 'sa_naive', 3, 2.0),
+]
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('N,m,algo,steps,G0', FIELD_CASES)
+def test_field_mode_equals_classic_mode(sq, N, m, algo, steps, G0, dtype):
+    """Field mode and classic mode run the same Markov chain: identical spins after every step on a quantised problem
+    (every sum exact), with the fields carried across steps (write-back) and with a per-step recomputation."""
+    W = quantized_symmetric_W(N, 4000 + N, dtype)
+    anns = []
+    for mode, refresh in (('classic', 0), ('field', 1), ('field', 1000)):
+        a = sq.dense_graph_annealer(W, sq.minimize, dtype, n_trotters=m, algorithm=algo)
+        a.set_sweep_mode(mode, refresh)
+        a.seed(77); a.prepare(); a.randomize_spin()
+        assert a.get_sweep_mode() == mode
+        anns.append(a)
+    G, beta = G0, 1. / 0.3
+    for s in range(steps):
+        for a in anns:
+            a.anneal_one_step(G, beta)
+        G *= 0.6
+        q0 = anns[0].get_spins()
+        for k, a in enumerate(anns[1:]):
+            qa = a.get_spins()
+            assert np.array_equal(qa, q0), 'step %d, variant %d: %d spins differ' % (s, k + 1, int((qa != q0).sum()))
+    acc = [a.get_stats()['accepted'] for a in anns]
+    assert acc[0] > 0 and acc[0] == acc[1] == acc[2]
+    # spins written from outside invalidate the carried fields
+    a = anns[2]
+    rng = np.random.default_rng(5)
+    qs = (2 * rng.integers(0, 2, (m, N)) - 1).astype(np.int8)
+    for b in (anns[0], a):
+        b.set_qset(qs)
+        b.anneal_one_step(G, beta)
+    assert np.array_equal(anns[0].get_spins(), a.get_spins())
+
+
+def test_field_mode_is_the_default_when_it_fits(sq):
+    W = quantized_symmetric_W(256, 5)
+    a = sq.dense_graph_annealer(W, sq.minimize, np.float32, n_trotters=64)
+    a.prepare()
+    assert a.get_sweep_mode() == 'field'
+    # 28 trotters per CTA x 2048 doubles do not fit: automatic mode falls back to the classic kernel, forcing field mode is an error
+    W = quantized_symmetric_W(2048, 6, np.float64)
+    b = sq.dense_graph_annealer(W, sq.minimize, np.float64, n_trotters=4000)
+    b.prepare()
+    assert b.get_sweep_mode() == 'classic'
+    c = sq.dense_graph_annealer(W, sq.minimize, np.float64, n_trotters=4000)
+    c.set_sweep_mode('field')
+    with pytest.raises(RuntimeError, match='shared memory'):
+        c.prepare()

@@ -244,7 +244,10 @@ def main():
                        'acceptance_rate': accepted / float(attempts_per_step * args.steps),
                        'flag_waits': stats1['flag_waits'] - stats0['flag_waits'],
                        'busy_ms_per_step_per_cta': {k: (stats1['barrier_cycles_' + k] - stats0['barrier_cycles_' + k]) / 148.0 / 1.965e6 / args.steps
-                                               for k in ('dot', 'chain')}},
+                                               for k in ('dot', 'chain')},
+                       # of the chain warp's time: waiting for the local fields of the next window / for the neighbouring CTAs' data
+                       'chain_wait_ms_per_step_per_cta': {k: (stats1['chain_wait_%s_cycles' % k] - stats0['chain_wait_%s_cycles' % k]) / 148.0 / 1.965e6 / args.steps
+                                                          for k in ('rows', 'neighbour')}},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'attempts/s', 'h2d_bytes_per_step': m * N, 'd2h_bytes_per_step': m * N + m * 4,
                     'steps': e2e_steps, 'E_min': float(np.min(E))},

@@ -49,7 +49,7 @@
 
 namespace sqb {
 
-enum { SW_MAX_K = 16, SW_DOT_WARPS = 12 /* chain-critical layout */, SW_DOT_WARPS_WIDE = 14 /* many trotters per CTA */, SW_THREADS = 512, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4, SW_TAB_SLOTS = 4,
+enum { SW_MAX_K = 16, SW_DOT_WARPS = 12 /* chain-critical layout */, SW_DOT_WARPS_WIDE = 14 /* many trotters per CTA */, SW_THREADS = 512, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4, SW_TAB_SLOTS = 4, SW_TAB_SLOTS_FIELD = 8 /* field mode prepares tables three windows ahead */,
        SW_CHAIN_WARP = 0, SW_SNAP_WARP = 4, SW_PREP_WARP = 8, SW_NB_WARP = 12 /* the dot warps are those with warp & 3 != 0 */ };
 
 template <class real> struct SweepParams {
@@ -99,15 +99,16 @@ template <class real> struct SweepSmem {
         nbsnap = o; o += (size_t)2 * 2 * nw64 * 8;
         dots = o; o += (size_t)2 * T * K * sizeof(real);
         o = (o + 15) & ~(size_t)15;
-        cross = o; o += (size_t)2 * T * K * (2 * K) * sizeof(real);
-        xs = o; o += (size_t)SW_TAB_SLOTS * T * K * 4;
-        xb = o; o += (size_t)SW_TAB_SLOTS * T * K * 4;
+        cross = o; o += (size_t)(fieldElems ? 4 : 2) * T * K * (2 * K) * sizeof(real); /* field mode gathers them a window ahead */
+        const size_t tab = fieldElems ? SW_TAB_SLOTS_FIELD : SW_TAB_SLOTS;
+        xs = o; o += tab * T * K * 4;
+        xb = o; o += tab * T * K * 4;
         o = (o + 15) & ~(size_t)15;
-        us = o; o += (size_t)SW_TAB_SLOTS * T * K * sizeof(real);
-        hs = o; o += (size_t)SW_TAB_SLOTS * T * K * sizeof(real);
-        xn = o; o += (size_t)2 * SW_TAB_SLOTS * K * 4;
+        us = o; o += tab * T * K * sizeof(real);
+        hs = o; o += tab * T * K * sizeof(real);
+        xn = o; o += (size_t)2 * tab * K * 4;
         conf = o; o += (size_t)2 * 2 * K * 4;
-        confAny = o; o += 16;
+        confAny = o; o += 32; /* + pubMask[2 buffers][2 sides] */
         accLog = o; o += (size_t)2 * T * 4;
         sgnLog = o; o += (size_t)2 * T * 4;
         o = (o + 15) & ~(size_t)15;
@@ -209,6 +210,7 @@ __device__ __forceinline__ int sweepPhase(int y, int m) { /* 0: even, 1: trotter
 template <class real, bool SQA, int K, bool FIELD>
 __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepParams<real> P) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int TAB = FIELD ? SW_TAB_SLOTS_FIELD : SW_TAB_SLOTS; /* slots of the per-window Philox tables */
     /* independent replicas of the same problem share J and h; seed, spins and hand-off block are per replica */
     const int replica = P.replicaBase + (int)blockIdx.y;
     const unsigned long long seedR = P.seed + (unsigned long long)replica;
@@ -255,6 +257,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     int *xn = reinterpret_cast<int *>(smem + L.xn);          /* [2 sides][3][K] */
     uint32_t *conf = reinterpret_cast<uint32_t *>(smem + L.conf);       /* [2 buffers][2 sides][K] */
     uint32_t *confAny = reinterpret_cast<uint32_t *>(smem + L.confAny); /* [2 buffers][2 sides]: rounds with a non-empty mask */
+    uint32_t *pubMask = confAny + 4; /* [2 buffers][2 sides]: rounds of my edge trotter whose accept flag the neighbouring CTA may read */
     uint32_t *accLog = reinterpret_cast<uint32_t *>(smem + L.accLog);   /* [2 buffers][maxT]: accept bits of a window */
     uint32_t *sgnLog = reinterpret_cast<uint32_t *>(smem + L.sgnLog);   /* [2 buffers][maxT]: spin (1 = up) before each attempt of a window */
     unsigned int *taskCounter = reinterpret_cast<unsigned int *>(smem + L.counter);
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     /* (x, -ln u, h[x]) of every attempt of window w for the owned trotters, plus the remote neighbours' x */
     auto prepWindow = [&](int w, int t0, int nthr) {
         if (w >= nW) return;
-        const int Kw = roundsIn(w), slot = w & (SW_TAB_SLOTS - 1);
+        const int Kw = roundsIn(w), slot = w & (TAB - 1);
         for (int idx = t0; idx < Kw * T; idx += nthr) {
             int t = idx % T, rl = idx / T;
             Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)gOf(y0 + t));
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             for (int idx = t0; idx < 2 * Kw; idx += nthr) {
                 int side = idx / Kw, rl = idx % Kw;
                 Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + rl), (uint32_t)(side ? yRight : yLeft));
-                xn[(side * SW_TAB_SLOTS + slot) * K + rl] = (int)(p.w[0] % (uint32_t)N);
+                xn[(side * TAB + slot) * K + rl] = (int)(p.w[0] % (uint32_t)N);
             }
         }
     };
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
      * Written to buffer wn & 1 while the chain replays window wn - 1 out of the other buffer. */
     auto neighbourWindow = [&](int wn) {
         if (!remote) return;
-        const int Kn = roundsIn(wn), slotN = wn & (SW_TAB_SLOTS - 1), bN = wn & 1;
+        const int Kn = roundsIn(wn), slotN = wn & (TAB - 1), bN = wn & 1;
         if (wn >= 2) {
             if (lane < 2) { /* lane 0 / 1 wait for the left / right neighbour's S_{wn-1} */
                 const int sl = lane ? slotR : slotL;
@@ -337,8 +340,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             uint32_t mask = 0;
             if (side < 2 && rl < Kn) {
                 const int xe = xs[(slotN * maxT + (side ? T - 1 : 0)) * K + rl];
-                const int *xp = xn + (side * SW_TAB_SLOTS + ((wn - 1) & (SW_TAB_SLOTS - 1))) * K;
-                const int *xc = xn + (side * SW_TAB_SLOTS + slotN) * K;
+                const int *xp = xn + (side * TAB + ((wn - 1) & (TAB - 1))) * K;
+                const int *xc = xn + (side * TAB + slotN) * K;
                 if (wn > 0) {
 #pragma unroll
                     for (int j = 0; j < K; ++j) mask |= (xp[j] == xe ? 1u : 0u) << j;
@@ -349,6 +352,18 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             }
             const uint32_t nz = __ballot_sync(0xffffffffu, mask != 0u);
             if (lane < 2) confAny[bN * 2 + lane] = (nz >> (lane * K)) & ((1u << K) - 1u);
+            /* the other direction: the neighbour reads the accept flag of my round j only when one of ITS attempts of this
+             * window or the next one draws the same spin index, so only those flags are ever published */
+            bool pub = (mask >> K) != 0u;
+            if (side < 2 && rl < Kn && wn + 1 < nW) {
+                const int xe = xs[(slotN * maxT + (side ? T - 1 : 0)) * K + rl];
+                const int *xq = xn + (side * TAB + ((wn + 1) & (TAB - 1))) * K;
+                const int Kq = roundsIn(wn + 1);
+#pragma unroll
+                for (int j = 0; j < K; ++j) pub |= (j < Kq && xq[j] == xe);
+            }
+            const uint32_t pb = __ballot_sync(0xffffffffu, pub);
+            if (lane < 2) pubMask[bN * 2 + lane] = (pb >> (lane * K)) & ((1u << K) - 1u);
         }
         __syncwarp();
     };
@@ -395,6 +410,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     prepWindow(0, tid, SW_THREADS);
     prepWindow(1, tid, SW_THREADS);
     prepWindow(2, tid, SW_THREADS);
+    if (FIELD) prepWindow(3, tid, SW_THREADS);
     real *const Fg = FIELD ? P.F + ((size_t)replica * m + y0) * P.ldF : NULL; /* this CTA's rows of the field matrix */
     if (FIELD) { /* ldF is a multiple of 128 elements: 16-byte copies */
         const int n16 = (int)((size_t)T * P.ldF * sizeof(real) / 16);
@@ -462,7 +478,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             const int iw = g / TPW, iid = g - iw * TPW;
             const int t = iid % T, rl = iid / T;
             if (ldAcquireCta(aPrepCount) > (uint32_t)iw) { /* the window's tables are already in place */
-                ix = xs[((iw & (SW_TAB_SLOTS - 1)) * maxT + t) * K + rl];
+                ix = xs[((iw & (TAB - 1)) * maxT + t) * K + rl];
             } else {
                 Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(iw * K + rl), (uint32_t)gOf(y0 + t));
                 ix = (int)(p.w[0] % (uint32_t)N);
@@ -478,12 +494,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
 
     /* reduce the row of task g (window w) against the snapshot the window is defined on; results go to buffer w & 1 */
     auto dotRow = [&](int g, int w) {
-        const int buf = w & 1, slot = w & (SW_TAB_SLOTS - 1);
+        const int buf = w & 1, slot = w & (TAB - 1);
         const int id = g - w * TPW;
         const int t = id % T, rl = id / T;
         /* column whose J[x][col] this lane must pick up: lane j < K -> round j of window w-1, else round j-K of w */
         int px = -1;
-        if (lane < K) { if (w > 0) px = xs[(((w - 1) & (SW_TAB_SLOTS - 1)) * maxT + t) * K + lane]; }
+        if (lane < K) { if (w > 0) px = xs[(((w - 1) & (TAB - 1)) * maxT + t) * K + lane]; }
         else if (lane < 2 * K && lane - K < rl) px = xs[(slot * maxT + t) * K + (lane - K)];
         real crossv = real(0);
         typename Acc4<real>::type acc;
@@ -533,7 +549,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             __syncwarp();
             if (lane < T) {
                 uint32_t bitsAcc = accLog[((w - 1) & 1) * maxT + lane];
-                const int *xbRow = xb + (((w - 1) & (SW_TAB_SLOTS - 1)) * maxT + lane) * K;
+                const int *xbRow = xb + (((w - 1) & (TAB - 1)) * maxT + lane) * K;
                 uint32_t *row = reinterpret_cast<uint32_t *>(dst + (size_t)lane * NW);
                 while (bitsAcc) {
                     const int rl = __ffs(bitsAcc) - 1;
@@ -586,7 +602,22 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     const int nDot = P.dotWarps;
     const int nGroups = FIELD ? (P.ldF >> 7) : 0;
     auto applyFlips = [&](int wf) {
-        const int wb = wf & 1, ws = wf & (SW_TAB_SLOTS - 1);
+        const int wb = wf & 1, ws = wf & (TAB - 1);
+        /* pass 1: pull this warp's 512-byte segments of every accepted row into L2 (no registers held), so that the
+         * read-modify-write pass below runs at L2 latency instead of one HBM round trip per flip */
+        for (int t = 0; t < T; ++t) {
+            uint32_t bits = accLog[wb * maxT + t];
+            while (bits) {
+                const int rl = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const real *Jrow = Jr + (size_t)xs[(ws * maxT + t) * K + rl] * P.ldJ;
+                const int perGroup = (int)(128 * sizeof(real) / 128); /* 128-byte lines per column group */
+                for (int i = lane; (dw + (i / perGroup) * nDot) < nGroups; i += 32) {
+                    const int g = dw + (i / perGroup) * nDot;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Jrow + (size_t)g * 128 + (size_t)(i % perGroup) * (128 / sizeof(real))));
+                }
+            }
+        }
         for (int t = 0; t < T; ++t) {
             uint32_t bits = accLog[wb * maxT + t];
             const uint32_t sg = sgnLog[wb * maxT + t];
@@ -615,62 +646,55 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         __syncwarp();
     };
     auto crossLoad = [&](int w, int e) -> real { /* lane j < K: J[x][x of round j of window w-1]; K <= j < 2K: round j-K of w */
-        const int slot = w & (SW_TAB_SLOTS - 1);
+        const int slot = w & (TAB - 1);
         const int t = e % T, rl = e / T;
         int px = -1;
-        if (lane < K) { if (w > 0) px = xs[(((w - 1) & (SW_TAB_SLOTS - 1)) * maxT + t) * K + lane]; }
+        if (lane < K) { if (w > 0) px = xs[(((w - 1) & (TAB - 1)) * maxT + t) * K + lane]; }
         else if (lane < 2 * K && lane - K < rl) px = xs[(slot * maxT + t) * K + (lane - K)];
         if (px < 0) return real(0);
         const int x = xs[(slot * maxT + t) * K + rl];
         return __ldg(Jr + (size_t)x * P.ldJ + px);
     };
-    auto fieldWindow = [&](int w) {
-        const int Kw = roundsIn(w), buf = w & 1, slot = w & (SW_TAB_SLOTS - 1);
-        const int nEnt = T * Kw;
-        uint32_t handled = 0;
-        real cv[4];
+    auto crossGather = [&](int w) { /* entry e -> warp e % nDot; lane j < 2K picks J[x][x_j]; buffer w & 3 */
+        const int nEnt = T * roundsIn(w), cb = w & 3;
+        for (int e0 = dw; e0 < nEnt; e0 += 8 * nDot) {
+            real cv[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { /* first batch of gathers in flight while the rows of the accepted flips stream */
-            const int e = dw + u * nDot;
-            cv[u] = (e < nEnt) ? crossLoad(w, e) : real(0);
-        }
-        if (w >= 2) applyFlips(w - 2);
-        for (int e0 = dw;;) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * nDot;
-                if (e < nEnt) {
-                    const int t = e % T, rl = e / T;
-                    if (lane < 2 * K) cross[((buf * maxT + t) * K + rl) * (2 * K) + lane] = cv[u];
-                    ++handled;
-                }
-            }
-            e0 += 4 * nDot;
-            if (e0 >= nEnt) break;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int e = e0 + u * nDot;
                 cv[u] = (e < nEnt) ? crossLoad(w, e) : real(0);
             }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * nDot;
+                if (e < nEnt && lane < 2 * K) cross[((cb * maxT + e % T) * K + e / T) * (2 * K) + lane] = cv[u];
+            }
         }
-        uint32_t mine = 0;
+    };
+    auto fieldWindow = [&](int w) {
+        const int Kw = roundsIn(w), buf = w & 1, slot = w & (TAB - 1);
+        const int nEnt = T * Kw;
+        if (w == 0) crossGather(0);
+        if (w >= 2) applyFlips(w - 2);
         for (int e = lane; e < nEnt; e += 32) {
             const int t = e % T, rl = e / T;
             const int o = (slot * maxT + t) * K + rl;
             const int x = xs[o];
-            if ((x >> 7) % nDot == dw) {
-                dots[(buf * maxT + t) * K + rl] = P.scaleA * (hs[o] + real(2) * field[(size_t)t * P.ldF + x]);
-                ++mine;
-            }
+            if ((x >> 7) % nDot == dw) dots[(buf * maxT + t) * K + rl] = P.scaleA * (hs[o] + real(2) * field[(size_t)t * P.ldF + x]);
         }
-        handled += __reduce_add_sync(0xffffffffu, mine);
-        __syncwarp(); /* every lane's dots / cross stores before lane 0's release */
-        if (lane == 0 && handled) redAddReleaseCta(aRowsDone + 4u * (uint32_t)buf, handled); /* the chain expects 2 per attempt */
+        /* one count per dot warp and window (parity buffers): the chain starts window w at nDot * (w / 2 + 1).  The release
+         * also covers the cross terms of window w, gathered at the end of the previous iteration */
+        __syncwarp();
+        if (lane == 0) redAddReleaseCta(aRowsDone + 4u * (uint32_t)buf, 1u);
+        if (w + 1 < nW) { /* off the chain's critical path: the cross terms of the NEXT window (they depend on the tables only) */
+            waitCount(aPrepCount, (uint32_t)w + 2u, 20);
+            crossGather(w + 1);
+        }
     };
 
     if (tid == 0) {
         stReleaseCta(aRowsDone, 0u); stReleaseCta(aRowsDone + 4, 0u); stReleaseCta(aReplayDone, 0u);
-        stReleaseCta(aSnapCount, 1u); stReleaseCta(aNbCount, 1u); stReleaseCta(aPrepCount, 3u);
+        stReleaseCta(aSnapCount, 1u); stReleaseCta(aNbCount, 1u); stReleaseCta(aPrepCount, FIELD ? 4u : 3u);
     }
     __syncthreads();
     const long long tLoop0 = clock64();
@@ -727,13 +751,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         for (int w = 1; w < nW; ++w) {
             waitCount(aReplayDone, (uint32_t)w, 20);
             snapshotWindow(w);
-            if (FIELD) { /* the dot warps read window w-2's table slot until window w's fields are out: neighbour data first */
+            if (FIELD) { /* eight table slots: window w+3 goes to the slot of window w-5, which nobody reads any more */
                 if (w + 1 < nW) { neighbourWindow(w + 1); signalCount(aNbCount, (uint32_t)w + 2u); }
-                if (w + 2 < nW) {
-                    waitCount(aRowsDone + 4u * (uint32_t)(w & 1), 2u * (uint32_t)((w >> 1) * TPW + roundsIn(w) * T), 20);
-                    prepWindow(w + 2, lane, 32);
-                    signalCount(aPrepCount, (uint32_t)w + 3u);
-                }
+                if (w + 3 < nW) { prepWindow(w + 3, lane, 32); signalCount(aPrepCount, (uint32_t)w + 4u); }
                 continue;
             }
             if (w + 2 < nW) { prepWindow(w + 2, lane, 32); signalCount(aPrepCount, (uint32_t)w + 3u); }
@@ -743,16 +763,15 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         /* the neighbours' S_{wn-1} and the conflict masks of window wn, into the buffers window wn-2 has finished with */
         for (int wn = 1; wn < nW; ++wn) {
             waitCount(aReplayDone, (uint32_t)(wn - 1), 20);
-            waitCount(aPrepCount, (uint32_t)wn + 1u, 20);
+            waitCount(aPrepCount, (uint32_t)min(wn + 2, nW), 20); /* the publish mask looks at the neighbour's next window too */
             neighbourWindow(wn);
             signalCount(aNbCount, (uint32_t)wn + 1u);
         }
     } else if (prepWarp) {
         /* tables of window wp go to the slot of window wp-4, dead once S_{wp-2} is built (window wp-3 replayed) */
-        for (int wp = 3; wp < nW; ++wp) {
-            waitCount(aSnapCount, (uint32_t)wp - 1u, 20);
-            if (FIELD) /* the dot warps read the slot of window wp-4 (its accepted flips) until the fields of window wp-2 are out */
-                waitCount(aRowsDone + 4u * (uint32_t)(wp & 1), 2u * (uint32_t)(((wp - 2) >> 1) * TPW + roundsIn(wp - 2) * T), 20);
+        for (int wp = FIELD ? 4 : 3; wp < nW; ++wp) {
+            /* field mode: eight slots, one more window of look-ahead (the dot warps still read window wp-4's slot then) */
+            waitCount(aSnapCount, (uint32_t)wp - (FIELD ? 2u : 1u), 20);
             prepWindow(wp, lane, 32);
             signalCount(aPrepCount, (uint32_t)wp + 1u);
         }
@@ -762,7 +781,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         const int tl = active ? lane : 0;
         const int gy = gOf(y0 + tl);             /* global trotter */
         const int myPhase = active ? sweepPhase(gy, mRing) : -1;
-        const bool oddRing = (mRing & 1) != 0;
+        int oddRingReg = mRing & 1; /* kept in a register: the compiler otherwise reloads it from the constant bank every round */
+        asm volatile("" : "+r"(oddRingReg));
+        const bool oddRing = oddRingReg != 0;
         const int yl = slotOf(gy == 0 ? mRing - 1 : gy - 1), yr = slotOf(gy == mRing - 1 ? 0 : gy + 1); /* slots of the neighbours */
         const bool lLocal = (yl >= y0 && yl < y0 + T), rLocal = (yr >= y0 && yr < y0 + T);
         const bool remoteLane = remote && active && (!lLocal || !rLocal);
@@ -783,11 +804,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         long long waitedNb = 0;
 
         for (int w = 0; w < nW; ++w) {
-            const int Kw = roundsIn(w), buf = w & 1, slot = w & (SW_TAB_SLOTS - 1);
+            const int Kw = roundsIn(w), buf = w & 1, slot = w & (TAB - 1);
             const unsigned long long *nbRows = nbsnap + (size_t)buf * 2 * NW;
             const uint32_t *confW = conf + buf * 2 * K;
             /* every row of this window reduced (and, through it, the window's tables in place); neighbour data in place */
-            waitCount(aRowsDone + 4u * (uint32_t)buf, (FIELD ? 2u : 1u) * (uint32_t)((w >> 1) * TPW + Kw * T), 0);
+            waitCount(aRowsDone + 4u * (uint32_t)buf, FIELD ? (uint32_t)(P.dotWarps * ((w >> 1) + 1)) : (uint32_t)((w >> 1) * TPW + Kw * T), 0);
             const long long waitedRows = waited;
             if (remote) waitCount(aNbCount, (uint32_t)w + 1u, 0);
             waitedNb += waited - waitedRows;
@@ -827,7 +848,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                     const uint32_t sg = __shfl_sync(0xffffffffu, sgnP, t);
                     if (i < T * K && rl < Kw && ev) {
                         const uint32_t aV = aDots + (uint32_t)(((buf * maxT + t) * K + rl) * sizeof(real));
-                        const uint32_t aC = aCross + (uint32_t)((((buf * maxT + t) * K + rl) * (2 * K)) * sizeof(real));
+                        const uint32_t aC = aCross + (uint32_t)(((((FIELD ? (w & 3) : buf) * maxT + t) * K + rl) * (2 * K)) * sizeof(real));
                         real v, c;
                         ldsReal(aV, v);
                         do {
@@ -848,10 +869,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             const uint32_t aRight = rLocal ? aRightLocal : aNb + (uint32_t)(buf * 2 + 1) * rowBytes;
             uint32_t cmask = 0; /* rounds in which a neighbour owned by another CTA attempts the same spin index */
             if (remoteLane) cmask = (lLocal ? 0u : confAny[buf * 2]) | (rLocal ? 0u : confAny[buf * 2 + 1]);
+            uint32_t pmask = 0; /* rounds whose accept flag a neighbouring CTA may read */
+            if (publishes) pmask = ((lane == 0 && !lLocal) ? pubMask[buf * 2] : 0u) | ((lane == T - 1 && !rLocal) ? pubMask[buf * 2 + 1] : 0u);
             uint32_t pXb = aXb + (uint32_t)(((slot * maxT + tl) * K) * 4);
             uint32_t pUs = aUs + (uint32_t)(((slot * maxT + tl) * K) * sizeof(real));
             uint32_t pDot = aDots + (uint32_t)(((buf * maxT + tl) * K) * sizeof(real));
-            uint32_t pCr = aCross + (uint32_t)((((buf * maxT + tl) * K) * (2 * K) + K) * sizeof(real)); /* this window's columns */
+            uint32_t pCr = aCross + (uint32_t)(((((FIELD ? (w & 3) : buf) * maxT + tl) * K) * (2 * K) + K) * sizeof(real)); /* this window's columns */
             const int tabBase = (slot * maxT + tl) * K;
             const unsigned long long flagBase = (P.roundBase + (unsigned long long)w * K + 1ull) << 1;
             int fs = (w * K) % SW_FLAG_RING;
@@ -908,7 +931,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                             accC |= 1u << rl;
                         }
                         sgnC |= up << rl;
-                        if (publishes) {
+                        if ((pmask >> rl) & 1u) {
                             const unsigned long long fv = flagBase + (unsigned long long)(2 * rl) + (acc ? 1ull : 0ull);
                             stRelaxed(myFlags + fs, fv);
                             if (mirror0) stRelaxedSys(mirror0 + fs, fv);
@@ -1260,6 +1283,9 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
                 if (forceK ? (k != forceK) : (k > 4 && (size_t)2 * maxT * k * 2 * k * sizeof(real) > (size_t)48 * 1024)) continue;
                 if (SweepSmem<real>(maxT, nw64, 128, 0, k, dotWarps_, ldJ_).total > dev_->smemPerBlockOptin()) continue;
                 fieldMode_ = true; K = k; chunkElems = 128; stages = 0;
+                /* the dot warps are lightly loaded in field mode and the accept chain paces the step: chain-critical layout
+                 * (chain alone with the three helper warps on scheduler 0) whatever the number of trotters per CTA */
+                if (!getenv("SQAOD_B200_SWEEP_WIDE")) dotWarps_ = SW_DOT_WARPS;
                 break;
             }
         }

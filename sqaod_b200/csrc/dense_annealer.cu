@@ -318,21 +318,38 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         if (!remote) return;
         const int Kn = roundsIn(wn), slotN = wn & (TAB - 1), bN = wn & 1;
         if (wn >= 2) {
-            if (lane < 2) { /* lane 0 / 1 wait for the left / right neighbour's S_{wn-1} */
+            /* S_{wn-1} of the two foreign neighbours = S_{wn-2} (the buffer window wn-1 uses) with the flips they accepted in
+             * window wn-2.  A neighbour hands those over as ONE 64-bit word per window -- tag << 16 | accept bits, written by
+             * its chain warp when the window ends; the spin indices are its Philox draws, which this CTA tabulates itself. */
+            const unsigned long long *srcB = nbsnap + (size_t)((bN ^ 1) * 2) * NW;
+            unsigned long long *dstB = nbsnap + (size_t)(bN * 2) * NW;
+            for (int i = lane; i < 2 * NW; i += 32) dstB[i] = srcB[i];
+            unsigned long long word = 0ull;
+            if (lane < 2) { /* lane 0 / 1 wait for the left / right neighbour's word of window wn-2 */
                 const int sl = lane ? slotR : slotL;
                 const unsigned long long want = P.snapBase + (unsigned long long)(wn - 1);
+                const unsigned long long *f = sBits + ((size_t)sl * SW_SNAP_SLOTS + ((wn - 2) % SW_SNAP_SLOTS)) * NW;
                 const long long t0 = clock64();
                 unsigned ns = 20;
-                if (ringSharded) { while (ldAcquireSys(sFlags + sl) < want) { ++nWaits; __nanosleep(ns); if (ns < 640u) ns <<= 1; } }
-                else { while (ldAcquire(sFlags + sl) < want) { ++nWaits; __nanosleep(ns); if (ns < 640u) ns <<= 1; } }
+                word = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f);
+                while ((word >> 16) != want) {
+                    ++nWaits;
+                    __nanosleep(ns);
+                    if (ns < 320u) ns <<= 1;
+                    word = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f);
+                }
                 if (lane == 0) waited += clock64() - t0;
             }
             __syncwarp();
-            for (int i = lane; i < 2 * NW; i += 32) {
-                const int side = i / NW, k = i - side * NW;
-                const int sl = side ? slotR : slotL;
-                nbsnap[(size_t)(bN * 2 + side) * NW + k] = __ldcg(sBits + ((size_t)sl * SW_SNAP_SLOTS + ((wn - 1) % SW_SNAP_SLOTS)) * NW + k);
+            const uint32_t mL = (uint32_t)__shfl_sync(0xffffffffu, word, 0) & 0xffffu, mR = (uint32_t)__shfl_sync(0xffffffffu, word, 1) & 0xffffu;
+            const int sideF = lane / K, jF = lane % K;
+            if (sideF < 2 && (((sideF ? mR : mL) >> jF) & 1u)) {
+                const int x = xn[(sideF * TAB + ((wn - 2) & (TAB - 1))) * K + jF];
+                int w64, bit;
+                spinBitPos(x, w64, bit);
+                atomicXor(reinterpret_cast<unsigned int *>(dstB + (size_t)sideF * NW + w64) + (bit >> 5), 1u << (bit & 31));
             }
+            __syncwarp();
         }
         {   /* lane -> (side, round of my edge trotter): which of the neighbour's 2K attempts (previous + this window) drew
              * the same spin index */
@@ -542,7 +559,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
 
     /* S_w for the dot warps (shared memory, double buffered) and for the neighbouring CTAs (global memory) */
     auto snapshotWindow = [&](int w) {
-        {   /* S_w = S_{w-1} with the accepted flips of window w-1 */
+        if (!FIELD) { /* S_w = S_{w-1} with the accepted flips of window w-1 (field mode has no use for snapshots) */
             const unsigned long long *src = qsnap + (size_t)((w - 1) & 1) * maxT * NW;
             unsigned long long *dst = qsnap + (size_t)(w & 1) * maxT * NW;
             for (int i = lane; i < T * NW; i += 32) dst[i] = src[i];
@@ -560,34 +577,6 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             }
         }
         signalCount(aSnapCount, (uint32_t)w + 1u);
-        if (remote) { /* publish the edge trotters' S_w for the neighbouring CTAs */
-            const unsigned long long *snapW = qsnap + (size_t)(w & 1) * maxT * NW;
-            const int nEdge = (T > 1) ? 2 : 1;
-            for (int i = lane; i < nEdge * NW; i += 32) {
-                const int e = i / NW, k = i - e * NW;
-                const int t = e ? T - 1 : 0;
-                const unsigned long long v = snapW[(size_t)t * NW + k];
-                const size_t off = (size_t)(w % SW_SNAP_SLOTS) * NW + k;
-                sBits[(size_t)(y0 + t) * SW_SNAP_SLOTS * NW + off] = v;
-                if (ringSharded) {
-                    if (y0 + t == 0 && P.peerSnapBits[0]) P.peerSnapBits[0][(size_t)(m + 1) * SW_SNAP_SLOTS * NW + off] = v;
-                    if (y0 + t == m - 1 && P.peerSnapBits[1]) P.peerSnapBits[1][(size_t)m * SW_SNAP_SLOTS * NW + off] = v;
-                }
-            }
-            /* the warp barrier orders every lane's stores before lane 0's release (cumulative), so no per-lane
-             * fence is needed inside the GPU; across GPUs keep the explicit system fence */
-            if (ringSharded) __threadfence_system();
-            __syncwarp();
-            if (lane == 0) {
-                const unsigned long long sv = P.snapBase + (unsigned long long)w;
-                stRelease(sFlags + y0, sv);
-                if (T > 1) stRelease(sFlags + y0 + T - 1, sv);
-                if (ringSharded) {
-                    if (y0 == 0 && P.peerSnapFlags[0]) stReleaseSys(P.peerSnapFlags[0] + m + 1, sv);
-                    if (y0 + T == m && P.peerSnapFlags[1]) stReleaseSys(P.peerSnapFlags[1] + m, sv);
-                }
-            }
-        }
     };
 
     /* ---------------- field mode: what the dot warps do instead of streaming one J row per attempt ----------------
@@ -772,6 +761,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         for (int wp = FIELD ? 4 : 3; wp < nW; ++wp) {
             /* field mode: eight slots, one more window of look-ahead (the dot warps still read window wp-4's slot then) */
             waitCount(aSnapCount, (uint32_t)wp - (FIELD ? 2u : 1u), 20);
+            if (!FIELD && remote) waitCount(aNbCount, (uint32_t)wp - 1u, 20); /* the neighbour warp reads window wp-4's draws for window wp-2 */
             prepWindow(wp, lane, 32);
             signalCount(aPrepCount, (uint32_t)wp + 1u);
         }
@@ -797,6 +787,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         /* the first / last trotter of a sharded ring also publishes into the neighbouring GPU's arrays */
         unsigned long long *mirror0 = (ringSharded && active && y0 + lane == 0 && P.peerFlags[0]) ? P.peerFlags[0] + (size_t)(m + 1) * SW_FLAG_RING : NULL;
         unsigned long long *mirror1 = (ringSharded && active && y0 + lane == m - 1 && P.peerFlags[1]) ? P.peerFlags[1] + (size_t)m * SW_FLAG_RING : NULL;
+        unsigned long long *const snapWord = sBits + (size_t)(y0 + tl) * SW_SNAP_SLOTS * NW; /* + (w & 3) * NW: this trotter's accept word of window w */
+        unsigned long long *snapMirror0 = (ringSharded && active && y0 + lane == 0 && P.peerSnapBits[0]) ? P.peerSnapBits[0] + (size_t)(m + 1) * SW_SNAP_SLOTS * NW : NULL;
+        unsigned long long *snapMirror1 = (ringSharded && active && y0 + lane == m - 1 && P.peerSnapBits[1]) ? P.peerSnapBits[1] + (size_t)m * SW_SNAP_SLOTS * NW : NULL;
         const real corrScale = real(-4) * P.scaleA; /* a flip of spin x' accepted since the snapshot changes sum by -2 q_old J[x][x'] */
         const real nbScale2 = real(2) * P.scaleNb;
         uint32_t accP = 0, sgnP = 0;
@@ -948,6 +941,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             if (active) {
                 accLog[buf * maxT + lane] = accC;
                 if (FIELD) sgnLog[buf * maxT + lane] = sgnC;
+            }
+            if (publishes) { /* the neighbouring CTAs (GPUs) rebuild this trotter's spins from the accept bits of the window */
+                const unsigned long long sv = ((P.snapBase + (unsigned long long)w + 1ull) << 16) | (unsigned long long)accC;
+                const size_t so = (size_t)(w % SW_SNAP_SLOTS) * NW;
+                stRelaxed(snapWord + so, sv);
+                if (snapMirror0) stRelaxedSys(snapMirror0 + so, sv);
+                if (snapMirror1) stRelaxedSys(snapMirror1 + so, sv);
             }
             nAccepted += (unsigned long long)__popc(accC);
             accP = accC; sgnP = sgnC;

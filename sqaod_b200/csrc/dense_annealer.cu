@@ -202,6 +202,26 @@ __device__ __forceinline__ void axpyRow4(double *F, double c, const RowVec4d &r)
     *(reinterpret_cast<double2 *>(F) + 1) = f1;
 }
 
+/* Rare path of the accept chain, kept out of line so that the hot loop stays small enough for the instruction cache: the
+ * spin of a trotter owned by another CTA -- published snapshot (one window old), corrected by the accept bits of exactly
+ * those of its attempts (bits of `mask`: j < K previous window, j >= K this window) that drew the same spin index. */
+__device__ __noinline__ int remoteSpinSlow(const unsigned long long *row, int x, uint32_t mask, long long rrBase, unsigned long long roundBase,
+                                           const unsigned long long *flags, int sys, unsigned long long *nWaits) {
+    int v = spinAt(row, x);
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const long long rr = rrBase + j;
+        const unsigned long long want = roundBase + (unsigned long long)rr + 1ull;
+        const unsigned long long *f = flags + (rr % SW_FLAG_RING);
+        /* the flag word carries its own payload (tag, accept bit): relaxed accesses are enough */
+        unsigned long long got = sys ? ldRelaxedSys(f) : ldRelaxed(f);
+        while ((got >> 1) != want) { ++*nWaits; __nanosleep(20); got = sys ? ldRelaxedSys(f) : ldRelaxed(f); }
+        if (got & 1ull) v = -v;
+    }
+    return v;
+}
+
 __device__ __forceinline__ int sweepPhase(int y, int m) { /* 0: even, 1: trotter m-1 of an odd ring, 2: odd */
     if (y & 1) return 2;
     return ((m & 1) && y == m - 1) ? 1 : 0;
@@ -771,9 +791,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         const int tl = active ? lane : 0;
         const int gy = gOf(y0 + tl);             /* global trotter */
         const int myPhase = active ? sweepPhase(gy, mRing) : -1;
-        int oddRingReg = mRing & 1; /* kept in a register: the compiler otherwise reloads it from the constant bank every round */
-        asm volatile("" : "+r"(oddRingReg));
-        const bool oddRing = oddRingReg != 0;
+        /* phases this CTA has to run per round: 0 and 2, plus 1 where trotter m-1 of an odd ring lives (a vote result, so
+         * that it stays in a register instead of being re-derived from the kernel parameters every round) */
+        const int phStep = __any_sync(0xffffffffu, myPhase == 1) ? 1 : 2;
         const int yl = slotOf(gy == 0 ? mRing - 1 : gy - 1), yr = slotOf(gy == mRing - 1 ? 0 : gy + 1); /* slots of the neighbours */
         const bool lLocal = (yl >= y0 && yl < y0 + T), rLocal = (yr >= y0 && yr < y0 + T);
         const bool remoteLane = remote && active && (!lLocal || !rLocal);
@@ -783,6 +803,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         const uint32_t aLeftLocal = smemAddr(qcur) + (uint32_t)(lLocal ? yl - y0 : 0) * rowBytes;
         const uint32_t aRightLocal = smemAddr(qcur) + (uint32_t)(rLocal ? yr - y0 : 0) * rowBytes;
         const uint32_t aNb = smemAddr(nbsnap), aDots = smemAddr(dots), aCross = smemAddr(cross), aXb = smemAddr(xb), aUs = smemAddr(us);
+        const uint32_t aXs = smemAddr(xs), aConf = smemAddr(conf);
+        const int nbPhaseL = sweepPhase(yLeft, mRing), nbPhaseR = sweepPhase(yRight, mRing);
         unsigned long long *myFlags = aFlags + (size_t)(y0 + tl) * SW_FLAG_RING;
         /* the first / last trotter of a sharded ring also publishes into the neighbouring GPU's arrays */
         unsigned long long *mirror0 = (ringSharded && active && y0 + lane == 0 && P.peerFlags[0]) ? P.peerFlags[0] + (size_t)(m + 1) * SW_FLAG_RING : NULL;
@@ -794,42 +816,17 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         const real nbScale2 = real(2) * P.scaleNb;
         uint32_t accP = 0, sgnP = 0;
         unsigned long long nAccepted = 0;
+        unsigned long long slowWaits = 0; /* flag polls of the out-of-line conflict path (its address is taken: lives in local memory) */
         long long waitedNb = 0;
 
         for (int w = 0; w < nW; ++w) {
             const int Kw = roundsIn(w), buf = w & 1, slot = w & (TAB - 1);
             const unsigned long long *nbRows = nbsnap + (size_t)buf * 2 * NW;
-            const uint32_t *confW = conf + buf * 2 * K;
             /* every row of this window reduced (and, through it, the window's tables in place); neighbour data in place */
             waitCount(aRowsDone + 4u * (uint32_t)buf, FIELD ? (uint32_t)(P.dotWarps * ((w >> 1) + 1)) : (uint32_t)((w >> 1) * TPW + Kw * T), 0);
             const long long waitedRows = waited;
             if (remote) waitCount(aNbCount, (uint32_t)w + 1u, 0);
             waitedNb += waited - waitedRows;
-
-            /* spin of a trotter owned by another CTA: published snapshot, corrected by the accept bits of the neighbour's
-             * attempts that hit the same spin index since the snapshot */
-            auto remoteSpin = [&](int side, int x, int rl) -> int {
-                int v = spinAt(nbRows + (size_t)side * NW, x);
-                uint32_t mask = confW[side * K + rl];
-                if (mask) {
-                    const int yn = side ? yRight : yLeft;
-                    const int nbPhase = sweepPhase(yn, mRing);
-                    uint32_t vis = (w > 0 ? ((1u << K) - 1u) : 0u) | (((1u << rl) - 1u) << K) | ((nbPhase < myPhase) ? (1u << (K + rl)) : 0u);
-                    mask &= vis;
-                    while (mask) {
-                        int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        long long rr = (long long)w * K + (j - K); /* j < K: previous window */
-                        const unsigned long long want = P.roundBase + (unsigned long long)rr + 1ull;
-                        const unsigned long long *f = aFlags + (size_t)(side ? slotR : slotL) * SW_FLAG_RING + (rr % SW_FLAG_RING);
-                        /* the flag word carries its own payload (tag, accept bit): relaxed accesses are enough */
-                        unsigned long long got = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f);
-                        while ((got >> 1) != want) { ++nWaits; __nanosleep(20); got = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f); }
-                        if (got & 1ull) v = -v;
-                    }
-                }
-                return v;
-            };
 
             /* 1. fold the flips of window w-1 into the snapshot dot products of window w: one (trotter, round) item per
              *    lane, so this is off the serial path */
@@ -856,8 +853,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 __syncwarp();
             }
 
-            /* 2. replay.  Per round: a phase-independent part (tables, repair with this window's own flips) for all lanes,
-             *    then the state-dependent core once per phase of the reference order (even y, [y = m-1 of an odd ring], odd y) */
+            /* 2. replay.  Per round: the state-independent part (tables) for all lanes, then the state-dependent core once per
+             *    phase of the reference order (even y, [y = m-1 of an odd ring], odd y) -- ONE copy of the core in a loop over
+             *    the phases, rare paths out of line, so that the loop fits the instruction cache -- then, if a flip was
+             *    accepted, the local fields of the trotter's later attempts in this window are repaired by all 32 lanes. */
             const uint32_t aLeft = lLocal ? aLeftLocal : aNb + (uint32_t)(buf * 2) * rowBytes;
             const uint32_t aRight = rLocal ? aRightLocal : aNb + (uint32_t)(buf * 2 + 1) * rowBytes;
             uint32_t cmask = 0; /* rounds in which a neighbour owned by another CTA attempts the same spin index */
@@ -867,9 +866,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             uint32_t pXb = aXb + (uint32_t)(((slot * maxT + tl) * K) * 4);
             uint32_t pUs = aUs + (uint32_t)(((slot * maxT + tl) * K) * sizeof(real));
             uint32_t pDot = aDots + (uint32_t)(((buf * maxT + tl) * K) * sizeof(real));
-            uint32_t pCr = aCross + (uint32_t)(((((FIELD ? (w & 3) : buf) * maxT + tl) * K) * (2 * K) + K) * sizeof(real)); /* this window's columns */
-            const int tabBase = (slot * maxT + tl) * K;
+            const uint32_t aDotsW = aDots + (uint32_t)((buf * maxT * K) * sizeof(real));                             /* dots of this window, [t][round] */
+            const uint32_t aCrossW = aCross + (uint32_t)(((FIELD ? (w & 3) : buf) * maxT * K * 2 * K + K) * sizeof(real)); /* this window's columns of [t][round][2K] */
+            const uint32_t aXsW = aXs + (uint32_t)(((slot * maxT + tl) * K) * 4);
+            const uint32_t aConfW = aConf + (uint32_t)((buf * 2 * K) * 4);
             const unsigned long long flagBase = (P.roundBase + (unsigned long long)w * K + 1ull) << 1;
+            const long long rrBase = (long long)w * K - K; /* round index of bit 0 of a conflict mask */
             int fs = (w * K) % SW_FLAG_RING;
             uint32_t accC = 0, sgnC = 0;
             uint32_t xbN = ldsU32(pXb);
@@ -880,62 +882,73 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             for (int rl = 0; rl < Kw; ++rl) {
                 const uint32_t aw = (xbN >> 5) << 2, bit = xbN & 31u;
                 const real lnu = lnuN;
-                real v = vN; /* scaleA (h + 2 sum) against the snapshot, flips of window w-1 included */
+                const real v = vN; /* scaleA (h + 2 sum) with every flip accepted so far folded in */
                 if (rl + 1 < Kw) { /* next round's table entries (state independent) */
                     pXb += 4; pUs += (uint32_t)sizeof(real); pDot += (uint32_t)sizeof(real);
                     xbN = ldsU32(pXb);
                     ldsReal(pUs, lnuN);
                     ldsReal(pDot, vN);
                 }
-                {   /* repair with this trotter's own flips earlier in this window */
-                    uint32_t ev = accC;
-                    while (ev) {
-                        const int j = __ffs(ev) - 1;
-                        ev &= ev - 1;
-                        real c;
-                        ldsReal(pCr + (uint32_t)(j * sizeof(real)), c);
-                        v += (((sgnC >> j) & 1u) ? corrScale : -corrScale) * c;
-                    }
-                }
-                pCr += (uint32_t)(2 * K * sizeof(real));
                 const bool conflict = (cmask >> rl) & 1u;
-
-                auto core = [&](int ph) {
+                bool accNow = false;
+                uint32_t upNow = 0;
+#pragma unroll 1
+                for (int ph = 0; ph < 3; ph += phStep) {
                     if (myPhase == ph) {
                         /* state-dependent shared-memory reads: own word and both neighbours' words */
                         const uint32_t wv = ldsU32(aMy + aw);
-                        const uint32_t up = (wv >> bit) & 1u;
+                        upNow = (wv >> bit) & 1u;
                         real vv = v;
                         if (SQA) {
                             const uint32_t lv = ldsU32(aLeft + aw), rv = ldsU32(aRight + aw);
                             int nb = (int)((lv >> bit) & 1u) + (int)((rv >> bit) & 1u); /* number of up neighbours */
                             if (conflict) { /* rare: a neighbour owned by another CTA attempted this very spin */
-                                const int x = xs[tabBase + rl];
+                                const int x = (int)ldsU32(aXsW + (uint32_t)rl * 4u);
                                 int ql = ((lv >> bit) & 1u) ? 1 : -1, qr = ((rv >> bit) & 1u) ? 1 : -1;
-                                if (!lLocal && confW[rl]) ql = remoteSpin(0, x, rl);
-                                if (!rLocal && confW[K + rl]) qr = remoteSpin(1, x, rl);
+                                /* visible: the previous window, earlier rounds of this one, this round if the neighbour's phase is earlier */
+                                const uint32_t visBase = (w > 0 ? ((1u << K) - 1u) : 0u) | (((1u << rl) - 1u) << K);
+                                const uint32_t mL = lLocal ? 0u : ldsU32(aConfW + (uint32_t)rl * 4u);
+                                const uint32_t mR = rLocal ? 0u : ldsU32(aConfW + (uint32_t)(K + rl) * 4u);
+                                if (mL) ql = remoteSpinSlow(nbRows, x, mL & (visBase | ((nbPhaseL < myPhase) ? (1u << (K + rl)) : 0u)), rrBase, P.roundBase,
+                                                            aFlags + (size_t)slotL * SW_FLAG_RING, ringSharded ? 1 : 0, &slowWaits);
+                                if (mR) qr = remoteSpinSlow(nbRows + NW, x, mR & (visBase | ((nbPhaseR < myPhase) ? (1u << (K + rl)) : 0u)), rrBase, P.roundBase,
+                                                            aFlags + (size_t)slotR * SW_FLAG_RING, ringSharded ? 1 : 0, &slowWaits);
                                 nb = (ql + qr + 2) >> 1;
                             }
                             vv -= nbScale2 * real(nb - 1);
                         }
-                        const bool acc = (up ? vv : -vv) < lnu; /* exp(-dE beta) > u */
-                        if (acc) {
-                            stsU32(aMy + aw, wv ^ (1u << bit));
-                            accC |= 1u << rl;
-                        }
-                        sgnC |= up << rl;
+                        accNow = (upNow ? vv : -vv) < lnu; /* exp(-dE beta) > u */
+                        if (accNow) stsU32(aMy + aw, wv ^ (1u << bit));
                         if ((pmask >> rl) & 1u) {
-                            const unsigned long long fv = flagBase + (unsigned long long)(2 * rl) + (acc ? 1ull : 0ull);
+                            const unsigned long long fv = flagBase + (unsigned long long)(2 * rl) + (accNow ? 1ull : 0ull);
                             stRelaxed(myFlags + fs, fv);
                             if (mirror0) stRelaxedSys(mirror0 + fs, fv);
                             if (mirror1) stRelaxedSys(mirror1 + fs, fv);
                         }
                     }
                     __syncwarp();
-                };
-                core(0);
-                if (oddRing) core(1);
-                core(2);
+                }
+                accC |= (accNow ? 1u : 0u) << rl;
+                sgnC |= upNow << rl;
+                /* an accepted flip of spin x changes the trotter's later local fields of this window by -4 scaleA q_old J[x'][x]:
+                 * lane r repairs round r (in the classic order of additions: flips in the order they were accepted) */
+                uint32_t accLanes = __ballot_sync(0xffffffffu, accNow);
+                if (accLanes) {
+                    do {
+                        const int t = __ffs(accLanes) - 1;
+                        accLanes &= accLanes - 1;
+                        const uint32_t upT = __shfl_sync(0xffffffffu, upNow, t);
+                        if (lane > rl && lane < Kw) {
+                            const uint32_t aV = aDotsW + (uint32_t)((t * K + lane) * sizeof(real));
+                            real dv, c;
+                            ldsReal(aV, dv);
+                            ldsReal(aCrossW + (uint32_t)(((t * K + lane) * 2 * K + rl) * sizeof(real)), c);
+                            stsReal(aV, dv + (upT ? corrScale : -corrScale) * c);
+                        }
+                    } while (accLanes);
+                    __syncwarp();
+                    if (rl + 1 < Kw) ldsReal(pDot, vN);
+                }
                 if (++fs == SW_FLAG_RING) fs = 0;
             }
             if (active) {
@@ -953,6 +966,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             accP = accC; sgnP = sgnC;
             signalCount(aReplayDone, (uint32_t)w + 1u);
         }
+        nWaits += slowWaits;
         if (P.stats) {
             nAccepted = warpSum(nAccepted);
             if (lane == 0) {

@@ -116,6 +116,7 @@ private:
     int dotWarps_ = 12;
     /* field mode of the sweep (dense_annealer.cu): local fields J.q kept in shared memory and updated per accepted flip */
     bool fieldMode_ = false;
+    bool specChain_ = true;        /* window-parallel accept chain (SQAOD_B200_SWEEP_SPEC=0: the sequential per-round chain) */
     DevBuf<real> dF_;              /* [m * replicas][ldJ] fields at step start */
     bool fieldsValid_ = false;     /* dF_ matches dq_ (cleared by everything that writes spins or the problem) */
     int fieldRefresh_ = 1, stepsSinceRefresh_ = 0; /* recompute F = J.q with the spin GEMM every fieldRefresh_ steps */

@@ -82,12 +82,13 @@ template <class real> struct SweepParams {
      * step start (spin GEMM or the previous step's write-back); kept in shared memory and updated incrementally by the sweep */
     real *F;
     int ldF, writeBackF;
+    int specChain; /* accept chain evaluates a whole window in parallel and commits flips in order (see the chain warp) */
     unsigned long long *stats;       /* [0] accepted flips, [1] remote wait polls, [2]/[3] busy cycles of dot warp 0 / the chain warp, summed over CTAs */
 };
 
 /* shared-memory carve-up, identical on host and device */
 template <class real> struct SweepSmem {
-    size_t field, ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, confAny, accLog, sgnLog, counter, total;
+    size_t field, ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, confAny, accLog, sgnLog, spec, counter, total;
     /* fieldElems > 0: field mode -- T rows of fieldElems local fields instead of the TMA ring (stages == 0) */
     __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K, int dotWarps, int fieldElems = 0) {
         size_t o = 0;
@@ -111,6 +112,7 @@ template <class real> struct SweepSmem {
         confAny = o; o += 32; /* + pubMask[2 buffers][2 sides] */
         accLog = o; o += (size_t)2 * T * 4;
         sgnLog = o; o += (size_t)2 * T * 4;
+        spec = o; o += (size_t)(2 * T + 2 * T * K) * 4; /* window-parallel chain: trotter info, frontiers, local conflict masks */
         o = (o + 15) & ~(size_t)15;
         counter = o; o += 32;
         total = (o + 127) & ~(size_t)127;
@@ -222,6 +224,22 @@ __device__ __noinline__ int remoteSpinSlow(const unsigned long long *row, int x,
     return v;
 }
 
+/* non-blocking variant for the window-parallel chain: spin bit (0 / 1), or -1 when one of the accept flags is not there yet */
+__device__ __noinline__ int remoteBitTry(const unsigned long long *row, int x, uint32_t mask, long long rrBase, unsigned long long roundBase,
+                                         const unsigned long long *flags, int sys) {
+    int v = spinAt(row, x) > 0 ? 1 : 0;
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const long long rr = rrBase + j;
+        const unsigned long long *f = flags + (rr % SW_FLAG_RING);
+        const unsigned long long got = sys ? ldRelaxedSys(f) : ldRelaxed(f);
+        if ((got >> 1) != roundBase + (unsigned long long)rr + 1ull) return -1;
+        v ^= (int)(got & 1ull);
+    }
+    return v;
+}
+
 __device__ __forceinline__ int sweepPhase(int y, int m) { /* 0: even, 1: trotter m-1 of an odd ring, 2: odd */
     if (y & 1) return 2;
     return ((m & 1) && y == m - 1) ? 1 : 0;
@@ -280,6 +298,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     uint32_t *pubMask = confAny + 4; /* [2 buffers][2 sides]: rounds of my edge trotter whose accept flag the neighbouring CTA may read */
     uint32_t *accLog = reinterpret_cast<uint32_t *>(smem + L.accLog);   /* [2 buffers][maxT]: accept bits of a window */
     uint32_t *sgnLog = reinterpret_cast<uint32_t *>(smem + L.sgnLog);   /* [2 buffers][maxT]: spin (1 = up) before each attempt of a window */
+    uint32_t *tinfo = reinterpret_cast<uint32_t *>(smem + L.spec);      /* [maxT]: phase | (left local index + 1) << 2 | (right local index + 1) << 8 */
+    uint32_t *front = tinfo + maxT;                                     /* [maxT]: rounds of the current window that are final */
+    uint32_t *lconf = front + maxT;                                     /* [maxT][2 sides][K]: rounds of the local neighbour drawing the same spin */
     unsigned int *taskCounter = reinterpret_cast<unsigned int *>(smem + L.counter);
 
     /* ring topology: local index l <-> global trotter (yOff + l) mod mRing */
@@ -799,7 +820,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         const bool remoteLane = remote && active && (!lLocal || !rLocal);
         const bool publishes = remote && active && (lane == 0 || lane == T - 1);
         const uint32_t rowBytes = (uint32_t)NW * 8u;
-        const uint32_t aMy = smemAddr(qcur) + (uint32_t)tl * rowBytes;
+        const uint32_t aMy0 = smemAddr(qcur);
+        const uint32_t aMy = aMy0 + (uint32_t)tl * rowBytes;
         const uint32_t aLeftLocal = smemAddr(qcur) + (uint32_t)(lLocal ? yl - y0 : 0) * rowBytes;
         const uint32_t aRightLocal = smemAddr(qcur) + (uint32_t)(rLocal ? yr - y0 : 0) * rowBytes;
         const uint32_t aNb = smemAddr(nbsnap), aDots = smemAddr(dots), aCross = smemAddr(cross), aXb = smemAddr(xb), aUs = smemAddr(us);
@@ -814,6 +836,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         unsigned long long *snapMirror1 = (ringSharded && active && y0 + lane == m - 1 && P.peerSnapBits[1]) ? P.peerSnapBits[1] + (size_t)m * SW_SNAP_SLOTS * NW : NULL;
         const real corrScale = real(-4) * P.scaleA; /* a flip of spin x' accepted since the snapshot changes sum by -2 q_old J[x][x'] */
         const real nbScale2 = real(2) * P.scaleNb;
+        if (active) tinfo[lane] = (uint32_t)myPhase | ((lLocal ? (uint32_t)(yl - y0 + 1) : 0u) << 2) | ((rLocal ? (uint32_t)(yr - y0 + 1) : 0u) << 8);
+        __syncwarp();
         uint32_t accP = 0, sgnP = 0;
         unsigned long long nAccepted = 0;
         unsigned long long slowWaits = 0; /* flag polls of the out-of-line conflict path (its address is taken: lives in local memory) */
@@ -874,6 +898,136 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             const long long rrBase = (long long)w * K - K; /* round index of bit 0 of a conflict mask */
             int fs = (w * K) % SW_FLAG_RING;
             uint32_t accC = 0, sgnC = 0;
+            if (P.specChain) {
+                /* Window-parallel accept chain.  Every attempt (t, r) of the window is evaluated at once -- lane = (trotter, round)
+                 * -- against the current spins and fields.  Per trotter, the attempts before its first "stop" are rejections whose
+                 * inputs were exact, so they are final; a stop is either an accept (committed: spin flipped, the trotter's later
+                 * fields repaired, frontier behind it) or an attempt that must wait because an EARLIER attempt of a neighbouring
+                 * trotter on the same spin index is not final yet (frontier stays in front of it).  Only accepted flips serialise:
+                 * the loop runs (accepted flips per trotter and window) + 1 times instead of once per round, and reproduces the
+                 * sequential reference order exactly. */
+                constexpr int TPP = 32 / K; /* trotters per pass */
+                const int nPass = (T + TPP - 1) / TPP;
+                const int rI = lane % K, jI = lane / K;
+                const int sysFlag = ringSharded ? 1 : 0;
+                const unsigned long long *nbRowsW = nbsnap + (size_t)buf * 2 * NW;
+                if (active) front[lane] = 0u;
+                if (SQA) {
+                    for (int pass = 0; pass < nPass; ++pass) { /* rounds of the local neighbours that draw the same spin index */
+                        const int t = pass * TPP + jI;
+                        if (t < T && rI < Kw) {
+                            const uint32_t info = tinfo[t];
+                            const int x = xs[(slot * maxT + t) * K + rI];
+#pragma unroll
+                            for (int side = 0; side < 2; ++side) {
+                                const int tn = (int)((info >> (2 + 6 * side)) & 63u) - 1;
+                                uint32_t msk = 0;
+                                if (tn >= 0) {
+                                    const int *xo = xs + (slot * maxT + tn) * K;
+#pragma unroll
+                                    for (int j = 0; j < K; ++j) msk |= ((j < Kw && xo[j] == x) ? 1u : 0u) << j;
+                                }
+                                lconf[(t * 2 + side) * K + rI] = msk;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                for (;;) {
+                    bool progress = false;
+                    for (int pass = 0; pass < nPass; ++pass) {
+                        const int t = pass * TPP + jI;
+                        const bool valid = (t < T) && (rI < Kw);
+                        bool stop = false, blk = false;
+                        uint32_t up = 0, wv = 0, aw = 0, bit = 0;
+                        if (valid && (uint32_t)rI >= front[t]) {
+                            const int o = (slot * maxT + t) * K + rI;
+                            const uint32_t xbv = (uint32_t)xb[o];
+                            aw = (xbv >> 5) << 2; bit = xbv & 31u;
+                            wv = ldsU32(aMy0 + (uint32_t)t * rowBytes + aw);
+                            up = (wv >> bit) & 1u;
+                            real vv = dots[(buf * maxT + t) * K + rI];
+                            if (SQA) {
+                                const uint32_t info = tinfo[t];
+                                const int ph = (int)(info & 3u);
+                                int nb = 0;
+#pragma unroll
+                                for (int side = 0; side < 2; ++side) {
+                                    const int tn = (int)((info >> (2 + 6 * side)) & 63u) - 1;
+                                    uint32_t nbit;
+                                    if (tn >= 0) {
+                                        nbit = (ldsU32(aMy0 + (uint32_t)tn * rowBytes + aw) >> bit) & 1u;
+                                        const uint32_t lm = lconf[(t * 2 + side) * K + rI];
+                                        if (lm) { /* rare: the neighbour draws this spin index in this window too */
+                                            const uint32_t prec = ((1u << rI) - 1u) | ((((int)(tinfo[tn] & 3u) < ph) ? 1u : 0u) << rI);
+                                            if (lm & prec & ~((1u << front[tn]) - 1u)) blk = true; /* an earlier one is not final yet */
+                                        }
+                                    } else {
+                                        nbit = (ldsU32(aNb + (uint32_t)(buf * 2 + side) * rowBytes + aw) >> bit) & 1u;
+                                        const uint32_t cm = conf[(buf * 2 + side) * K + rI];
+                                        if (cm) { /* rare: so does the neighbour owned by another CTA -- its accept flags decide */
+                                            const uint32_t prec = (w > 0 ? ((1u << K) - 1u) : 0u) | (((1u << rI) - 1u) << K) |
+                                                                  ((((side ? nbPhaseR : nbPhaseL) < ph) ? 1u : 0u) << (K + rI));
+                                            if (cm & prec) {
+                                                const int rb = remoteBitTry(nbRowsW + (size_t)side * NW, xs[o], cm & prec, rrBase, P.roundBase,
+                                                                            aFlags + (size_t)(side ? slotR : slotL) * SW_FLAG_RING, sysFlag);
+                                                if (rb < 0) blk = true; else nbit = (uint32_t)rb;
+                                            }
+                                        }
+                                    }
+                                    nb += (int)nbit;
+                                }
+                                vv -= nbScale2 * real(nb - 1);
+                            }
+                            stop = blk || ((up ? vv : -vv) < us[o]); /* exp(-dE beta) > u */
+                        }
+                        const uint32_t stopBits = __ballot_sync(0xffffffffu, stop), blkBits = __ballot_sync(0xffffffffu, blk);
+                        const uint32_t upBits = __ballot_sync(0xffffffffu, up != 0u);
+#pragma unroll
+                        for (int j = 0; j < TPP; ++j) {
+                            const int tj = pass * TPP + j;
+                            if (tj >= T) break;
+                            const uint32_t h = (stopBits >> (j * K)) & ((K == 32) ? 0xffffffffu : ((1u << K) - 1u));
+                            const int rs = h ? (__ffs(h) - 1) : Kw;
+                            const bool commit = h && !((blkBits >> (j * K + rs)) & 1u);
+                            const uint32_t oldFront = front[tj];
+                            const uint32_t newFront = (uint32_t)(commit ? rs + 1 : rs);
+                            progress |= (newFront != oldFront);
+                            __syncwarp(); /* everybody has read front[tj] */
+                            uint32_t upj = 0;
+                            if (commit) {
+                                upj = (upBits >> (j * K + rs)) & 1u;
+                                if (lane == j * K + rs) stsU32(aMy0 + (uint32_t)tj * rowBytes + aw, wv ^ (1u << bit));
+                                if (lane > rs && lane < Kw) { /* the trotter's later local fields of this window */
+                                    const uint32_t aV = aDotsW + (uint32_t)((tj * K + lane) * sizeof(real));
+                                    real dv, c;
+                                    ldsReal(aV, dv);
+                                    ldsReal(aCrossW + (uint32_t)(((tj * K + lane) * 2 * K + rs) * sizeof(real)), c);
+                                    stsReal(aV, dv + (upj ? corrScale : -corrScale) * c);
+                                }
+                            }
+                            if (lane == tj) { /* the trotter's own lane keeps its logs, frontier and published flags */
+                                if (commit) { accC |= 1u << rs; sgnC |= upj << rs; }
+                                uint32_t pend = pmask & ((1u << newFront) - 1u) & ~((1u << oldFront) - 1u);
+                                while (pend) { /* rounds that became final and whose accept flag a neighbouring CTA may read */
+                                    const int r = __ffs(pend) - 1;
+                                    pend &= pend - 1;
+                                    const unsigned long long fv = flagBase + (unsigned long long)(2 * r) + ((commit && r == rs) ? 1ull : 0ull);
+                                    const int fsr = (fs + r) % SW_FLAG_RING;
+                                    stRelaxed(myFlags + fsr, fv);
+                                    if (mirror0) stRelaxedSys(mirror0 + fsr, fv);
+                                    if (mirror1) stRelaxedSys(mirror1 + fsr, fv);
+                                }
+                                front[tj] = newFront;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    const bool mineDone = !active || front[lane] >= (uint32_t)Kw;
+                    if (__all_sync(0xffffffffu, mineDone)) break;
+                    if (!progress) { ++nWaits; __nanosleep(20); } /* everything left waits for another CTA's accept flag */
+                }
+            } else {
             uint32_t xbN = ldsU32(pXb);
             real lnuN, vN;
             ldsReal(pUs, lnuN);
@@ -951,6 +1105,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 }
                 if (++fs == SW_FLAG_RING) fs = 0;
             }
+            } /* sequential chain */
             if (active) {
                 accLog[buf * maxT + lane] = accC;
                 if (FIELD) sgnLog[buf * maxT + lane] = sgnC;
@@ -1314,6 +1469,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     nw64_ = nw64;
     smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages, K, dotWarps_, fieldMode_ ? ldJ_ : 0).total;
     nWindows_ = (N_ + K - 1) / K;
+    specChain_ = getenv("SQAOD_B200_SWEEP_SPEC") ? atoi(getenv("SQAOD_B200_SWEEP_SPEC")) != 0 : true;
     fieldsValid_ = false;
     if (fieldMode_) {
         dF_.alloc(dev_, (size_t)rows * ldJ_);
@@ -1514,6 +1670,7 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
     P.snapBase = (launchCount_ + 1ull) * (unsigned long long)(nWindows_ + 2);
     P.stats = dStats_.p;
     P.F = NULL; P.ldF = 0; P.writeBackF = 0;
+    P.specChain = specChain_ ? 1 : 0;
     if (fieldMode_) {
         if (!fieldsValid_ || stepsSinceRefresh_ >= fieldRefresh_) refreshFields();
         ++stepsSinceRefresh_;

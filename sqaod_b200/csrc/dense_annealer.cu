@@ -1469,7 +1469,9 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     nw64_ = nw64;
     smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages, K, dotWarps_, fieldMode_ ? ldJ_ : 0).total;
     nWindows_ = (N_ + K - 1) / K;
-    specChain_ = getenv("SQAOD_B200_SWEEP_SPEC") ? atoi(getenv("SQAOD_B200_SWEEP_SPEC")) != 0 : true;
+    /* measured at C2: the window-parallel chain wins where the dot warps pace the step (classic mode, 13.8 vs 15.3 ms), the
+     * per-round chain where the chain itself does (field mode, 4.05 vs 4.7 ms) */
+    specChain_ = getenv("SQAOD_B200_SWEEP_SPEC") ? atoi(getenv("SQAOD_B200_SWEEP_SPEC")) != 0 : !fieldMode_;
     fieldsValid_ = false;
     if (fieldMode_) {
         dF_.alloc(dev_, (size_t)rows * ldJ_);

@@ -259,6 +259,10 @@ def main():
                          # the part of the algorithmic bytes that really came from HBM (ncu dram bytes per launch, profiles/):
                          # frac > 1 on the algorithmic figure is L2 reuse of J rows (classic mode) or rows of rejected attempts
                          # that were never needed (field mode: incremental local fields), not skipped work
+                         'note': ('field mode is paced by the latency of the accept chain (one warp per CTA, ~430 ns per round), not by HBM: '
+                                  'achieved/frac are the SURVEY 8d algorithmic figure (one J row per attempt, rows of rejected attempts '
+                                  'are never fetched), dram_GBps/dram_frac the bytes the kernel really moves (ncu, profiles/)') if mode == 'field'
+                                 else 'classic mode streams one J row per attempt and is HBM-bound; achieved > dram_GBps is L2 reuse of rows',
                          'dram_GBps': (traffic / (ms / args.steps * 1e-3) / 1e9) if traffic else None,
                          'dram_frac': (traffic / (ms / args.steps * 1e-3) / 1e9 / peak) if traffic else None},
         }

@@ -6,11 +6,13 @@ rng = np.random.default_rng(3)
 for N, m, dt in ((300, 296, np.float32), (72, 1800, np.float32), (2100, 12, np.float64), (40, 4001, np.float64), (130, 1, np.float32)):
     A = rng.random((N, N)) - 0.5
     W = (np.triu(A) + np.triu(A, 1).T).astype(dt)
-    ann = sq.dense_graph_annealer(W, sq.minimize, dt, n_trotters=m)
-    ann.seed(7); ann.prepare(); ann.randomize_spin()
-    for _ in range(2):
-        ann.anneal_one_step(1.0, 2.0)
-    print(N, m, dt.__name__, float(ann.get_E().min()))
+    for mode, refresh in (('classic', 0), ('field', 0), ('field', 1000)):   # both sweep kernels, fields recomputed / carried
+        ann = sq.dense_graph_annealer(W, sq.minimize, dt, n_trotters=m)
+        ann.set_sweep_mode(mode, refresh)
+        ann.seed(7); ann.prepare(); ann.randomize_spin()
+        for _ in range(2):
+            ann.anneal_one_step(1.0, 2.0)
+        print(N, m, dt.__name__, mode, refresh, float(ann.get_E().min()))
 
 # bipartite annealer (tcgen05 contraction for fp32, CUDA-core for fp64), brute-force searchers, formulas
 for N0, N1, m, dt in ((70, 45, 9, np.float32), (33, 64, 6, np.float64)):

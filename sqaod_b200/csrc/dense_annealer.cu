@@ -34,7 +34,21 @@
  *     warp 12 does the three helper jobs in turn.
  *   - inside the CTA there is no barrier in the sweep either: the warps hand work over through five release/acquire
  *     counters in shared memory (see the kernel body).
- * HBM traffic is one J row per attempt (N*sizeof(real) bytes), the figure SURVEY.md section 8(d) uses.
+ * HBM traffic of this "classic" form is one J row per attempt (N*sizeof(real) bytes), the figure SURVEY.md section 8(d) uses.
+ *
+ * FIELD mode (template flag FIELD; the north star's "local-field update kept incrementally in shared memory"): the local fields
+ * F[y][j] = sum_i J[j][i] q[y][i] of every trotter are computed once per step by the tcgen05 spin GEMM (energy_tc.cu; CUDA-core
+ * GEMM for fp64), loaded into shared memory (T rows of N reals per CTA) and updated with one J row per ACCEPTED flip, two
+ * windows behind the chain; the look-ahead machinery (cross terms, fold, repair) bridges those two windows exactly as it
+ * bridges the snapshot lag of the classic form, so both forms run the same Markov chain bit for bit.  The dot warps turn into
+ * "field warps": they own column groups of the field rows, stream the rows of accepted flips (L2 prefetch + 128-bit loads),
+ * gather the <= 2K-1 cross terms J[x][x'] of every attempt with 4-byte loads a window ahead, and hand the chain
+ * scaleA (h[x] + 2 F[y][x]).  Traffic drops from one row per attempt to (acceptance rate) rows + 31 sectors per attempt.
+ *
+ * CTAs meet through (a) one 64-bit word per edge trotter and window (tag << 16 | accept bits) from which the neighbouring CTA
+ * rebuilds the trotter's spins with its own copy of the Philox draws, and (b) per-attempt accept flags, published only for
+ * the rounds in which the neighbour can draw the same spin index.  Both are mirrored to the neighbouring GPU when the ring is
+ * sharded.
  */
 #include "device.hpp"
 #include "kernels_common.cuh"
@@ -1440,12 +1454,17 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
                 }
             }
         }
-        /* Field mode: no TMA ring, T rows of local fields instead.  Chosen whenever the rows fit next to the tables (the
-         * traffic is acceptance-rate x one J row per attempt instead of one row per attempt); SQAOD_B200_SWEEP_FIELD=0/1
-         * overrides.  Not combined with ring sharding or problem batches. */
+        /* Field mode: no TMA ring, T rows of local fields instead (traffic: acceptance rate x one J row per attempt instead of
+         * one row per attempt).  Automatic choice, from the size sweep in benchmarks/README.md: when the rows fit next to the
+         * tables AND either J is too large for L2 (the classic kernel is then HBM-bound: C2 3.9 vs 14 ms) or a CTA carries 3-4
+         * trotters (N = m = 512: 0.32 vs 0.39 ms); with 1-2 trotters per CTA the classic kernel's look-ahead dot products already
+         * hide behind the chain, and with many trotters per CTA the field warps' per-window work (cross-term gathers, T K of
+         * them) outweighs the saved rows (N = m = 1024 / 2048: 1.1 / 5.2 vs 0.9 / 4.1 ms).  set_sweep_mode() or
+         * SQAOD_B200_SWEEP_FIELD=0/1 override.  Not combined with ring sharding or problem batches. */
         fieldMode_ = false;
         const char *fe = getenv("SQAOD_B200_SWEEP_FIELD");
-        const bool fieldWanted = (sweepModeWanted_ >= 0) ? sweepModeWanted_ != 0 : (fe ? atoi(fe) != 0 : true);
+        const bool fieldAuto = ((size_t)N_ * ldJ_ * sizeof(real) > ((size_t)64 << 20)) || (maxT >= 3 && maxT <= 4);
+        const bool fieldWanted = (sweepModeWanted_ >= 0) ? sweepModeWanted_ != 0 : (fe ? atoi(fe) != 0 : fieldAuto);
         sqb_throwErrorIf(sweepModeWanted_ == 1 && (ringWorld_ > 1 || nProblems_ > 1), "field mode cannot be combined with ring sharding or problem batches.");
         if (fieldWanted && ringWorld_ <= 1 && nProblems_ <= 1) {
             for (int k = SW_MAX_K; k >= 4; k >>= 1) {
@@ -1469,9 +1488,10 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     nw64_ = nw64;
     smemBytes_ = SweepSmem<real>(maxT, nw64, chunkElems, stages, K, dotWarps_, fieldMode_ ? ldJ_ : 0).total;
     nWindows_ = (N_ + K - 1) / K;
-    /* measured at C2: the window-parallel chain wins where the dot warps pace the step (classic mode, 13.8 vs 15.3 ms), the
-     * per-round chain where the chain itself does (field mode, 4.05 vs 4.7 ms) */
-    specChain_ = getenv("SQAOD_B200_SWEEP_SPEC") ? atoi(getenv("SQAOD_B200_SWEEP_SPEC")) != 0 : !fieldMode_;
+    /* accept chain: the window-parallel form pays off with 1-2 trotters per CTA in the classic kernel (N = m = 128 / 256: 0.076 /
+     * 0.146 vs 0.10 / 0.18 ms per step); with more trotters per CTA the per-round chain, which handles all of them in one
+     * warp instruction stream, is faster (N = m = 1024: 0.89 vs 1.46 ms), and so it is in field mode (C2: 3.9 vs 4.7 ms) */
+    specChain_ = getenv("SQAOD_B200_SWEEP_SPEC") ? atoi(getenv("SQAOD_B200_SWEEP_SPEC")) != 0 : (!fieldMode_ && maxT <= 2);
     fieldsValid_ = false;
     if (fieldMode_) {
         dF_.alloc(dev_, (size_t)rows * ldJ_);

@@ -53,6 +53,12 @@ def test_host_side_preferences_and_errors(lib, dt):
     assert b'Device not set' in L.sqb_last_error()
     assert L.sqb_dg_annealer_prepare(h, dt) != 0 and b'Problem is not set' in L.sqb_last_error()
     assert L.sqb_dg_annealer_anneal_one_step(h, C.c_double(1.), C.c_double(1.), dt) != 0
+    # sweep-mode selector (host-side state only; takes effect at prepare()): -1 automatic, 0 classic, 1 field
+    for mode in (-1, 0, 1):
+        assert L.sqb_dg_annealer_set_sweep_mode(h, mode, 0, dt) == 0
+    assert L.sqb_dg_annealer_set_sweep_mode(h, 2, 0, dt) != 0 and b'sweep mode' in L.sqb_last_error()
+    mode = C.c_int(7)
+    assert L.sqb_dg_annealer_get_sweep_mode(h, C.byref(mode), dt) == 0 and mode.value == 0      # nothing prepared yet
     assert L.sqb_dg_annealer_delete(h, dt) == 0
     # brute-force searcher: tile sizes are rounded up to multiples of 256 (Solver.cpp:205)
     s = C.c_void_p()

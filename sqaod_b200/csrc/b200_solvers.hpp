@@ -118,6 +118,7 @@ private:
     bool fieldMode_ = false;
     bool specChain_ = true;        /* window-parallel accept chain (SQAOD_B200_SWEEP_SPEC=0: the sequential per-round chain) */
     DevBuf<real> dF_;              /* [m * replicas][ldJ] fields at step start */
+    DevBuf<real> dRowMax_;         /* [N] max_j |J[i][j]| (field mode) */
     bool fieldsValid_ = false;     /* dF_ matches dq_ (cleared by everything that writes spins or the problem) */
     int fieldRefresh_ = 1, stepsSinceRefresh_ = 0; /* recompute F = J.q with the spin GEMM every fieldRefresh_ steps */
     int sweepModeWanted_ = -1, fieldRefreshWanted_ = 0; /* setSweepMode(); -1 / 0: automatic */

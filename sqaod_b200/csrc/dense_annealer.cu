@@ -64,7 +64,10 @@
 namespace sqb {
 
 enum { SW_MAX_K = 16, SW_DOT_WARPS = 12 /* chain-critical layout */, SW_DOT_WARPS_WIDE = 14 /* many trotters per CTA */, SW_THREADS = 512, SW_FLAG_RING = 128, SW_SNAP_SLOTS = 4, SW_TAB_SLOTS = 4, SW_TAB_SLOTS_FIELD = 8 /* field mode prepares tables three windows ahead */,
-       SW_CHAIN_WARP = 0, SW_SNAP_WARP = 4, SW_PREP_WARP = 8, SW_NB_WARP = 12 /* the dot warps are those with warp & 3 != 0 */ };
+       SW_CHAIN_WARP = 0, SW_SNAP_WARP = 4, SW_PREP_WARP = 8, SW_NB_WARP = 12 /* the dot warps are those with warp & 3 != 0 */,
+       /* field mode: warps 0-3 are accept-chain warps (one per scheduler, trotter t -> warp t % 4), warp 4 does all the helper
+        * work, warps 5-15 own the column groups of the field rows */
+       SW_FIELD_CHAIN_WARPS = 4, SW_FIELD_HELPER_WARP = 4, SW_FIELD_WARPS = 11 };
 
 template <class real> struct SweepParams {
     const real *J;
@@ -96,13 +99,14 @@ template <class real> struct SweepParams {
      * step start (spin GEMM or the previous step's write-back); kept in shared memory and updated incrementally by the sweep */
     real *F;
     int ldF, writeBackF;
+    const real *rowMax; /* field mode: max_j |J[i][j]| per row -- bounds a cross term whose gather is still in flight */
     int specChain; /* accept chain evaluates a whole window in parallel and commits flips in order (see the chain warp) */
     unsigned long long *stats;       /* [0] accepted flips, [1] remote wait polls, [2]/[3] busy cycles of dot warp 0 / the chain warp, summed over CTAs */
 };
 
 /* shared-memory carve-up, identical on host and device */
 template <class real> struct SweepSmem {
-    size_t field, ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, confAny, accLog, sgnLog, spec, counter, total;
+    size_t field, ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, rmx, xn, conf, confAny, accLog, sgnLog, spec, carry, pend, cstate, counter, total;
     /* fieldElems > 0: field mode -- T rows of fieldElems local fields instead of the TMA ring (stages == 0) */
     __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K, int dotWarps, int fieldElems = 0) {
         size_t o = 0;
@@ -110,23 +114,30 @@ template <class real> struct SweepSmem {
         ring = o; o += (size_t)dotWarps * stages * chunkElems * sizeof(real);
         bars = o; o += (size_t)dotWarps * stages * 8;
         qcur = o; o += (size_t)T * nw64 * 8;
-        qsnap = o; o += (size_t)2 * T * nw64 * 8;
+        qsnap = o; o += (size_t)(fieldElems ? 0 : 2) * T * nw64 * 8; /* field mode has no use for snapshots */
         nbsnap = o; o += (size_t)2 * 2 * nw64 * 8;
         dots = o; o += (size_t)2 * T * K * sizeof(real);
         o = (o + 15) & ~(size_t)15;
-        cross = o; o += (size_t)(fieldElems ? 4 : 2) * T * K * (2 * K) * sizeof(real); /* field mode gathers them a window ahead */
+        cross = o; o += (size_t)(fieldElems ? 0 : 2) * T * K * (2 * K) * sizeof(real); /* field mode gathers cross terms per ACCEPTED flip */
         const size_t tab = fieldElems ? SW_TAB_SLOTS_FIELD : SW_TAB_SLOTS;
         xs = o; o += tab * T * K * 4;
         xb = o; o += tab * T * K * 4;
         o = (o + 15) & ~(size_t)15;
         us = o; o += tab * T * K * sizeof(real);
         hs = o; o += tab * T * K * sizeof(real);
+        rmx = o; o += (fieldElems ? tab : 0) * T * K * sizeof(real);
         xn = o; o += (size_t)2 * tab * K * 4;
         conf = o; o += (size_t)2 * 2 * K * 4;
         confAny = o; o += 32; /* + pubMask[2 buffers][2 sides] */
         accLog = o; o += (size_t)2 * T * 4;
         sgnLog = o; o += (size_t)2 * T * 4;
         spec = o; o += (size_t)(2 * T + 2 * T * K) * 4; /* window-parallel chain: trotter info, frontiers, local conflict masks */
+        o = (o + 15) & ~(size_t)15;
+        /* field mode: carry[T][K] = corrections already known for the NEXT window's attempts; pend[T][32] = landing slots of the
+         * cross-term gathers in flight; cstate[T][8] = per-trotter chain state (pending generation, accept / sign logs) */
+        carry = o; o += (size_t)(fieldElems ? 1 : 0) * T * K * sizeof(real);
+        pend = o; o += (size_t)(fieldElems ? 1 : 0) * T * 32 * sizeof(real);
+        cstate = o; o += (size_t)(fieldElems ? 1 : 0) * T * 8 * sizeof(real);
         o = (o + 15) & ~(size_t)15;
         counter = o; o += 32;
         total = (o + 127) & ~(size_t)127;
@@ -276,13 +287,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     /* warp roles.  Warps are spread over the SM's four schedulers by (warp & 3): scheduler 0 is kept for the latency-bound
      * accept chain and its helpers, the twelve streaming dot warps share the other three. */
-    const bool wide = (P.dotWarps == SW_DOT_WARPS_WIDE);
-    const bool dotWarp = (warp & 3) != 0 || (wide && (warp == SW_SNAP_WARP || warp == SW_PREP_WARP));
-    /* dot warp index: 0..11 for the warps of schedulers 1-3, 12 / 13 for warps 4 / 8 in the wide layout */
-    const int dw = (warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : SW_DOT_WARPS + (warp >> 2) - 1;
-    const bool chainWarp = (warp == SW_CHAIN_WARP);
-    const bool snapWarp = !wide && (warp == SW_SNAP_WARP), prepWarp = !wide && (warp == SW_PREP_WARP), nbWarp = !wide && (warp == SW_NB_WARP);
-    const bool allHelperWarp = wide && (warp == SW_NB_WARP); /* wide layout: warp 12 builds snapshots, tables and neighbour data in turn */
+    const bool wide = !FIELD && (P.dotWarps == SW_DOT_WARPS_WIDE);
+    const bool dotWarp = FIELD ? (warp > SW_FIELD_HELPER_WARP) : ((warp & 3) != 0 || (wide && (warp == SW_SNAP_WARP || warp == SW_PREP_WARP)));
+    /* dot warp index: 0..11 for the warps of schedulers 1-3, 12 / 13 for warps 4 / 8 in the wide layout; field mode: warps 5..15 */
+    const int dw = FIELD ? warp - (SW_FIELD_HELPER_WARP + 1) : ((warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : SW_DOT_WARPS + (warp >> 2) - 1);
+    const bool chainWarp = FIELD ? (warp < SW_FIELD_CHAIN_WARPS) : (warp == SW_CHAIN_WARP);
+    const bool snapWarp = !FIELD && !wide && (warp == SW_SNAP_WARP), prepWarp = !FIELD && !wide && (warp == SW_PREP_WARP), nbWarp = !FIELD && !wide && (warp == SW_NB_WARP);
+    /* wide layout: warp 12 builds snapshots, tables and neighbour data in turn; field mode: warp 4 does */
+    const bool allHelperWarp = FIELD ? (warp == SW_FIELD_HELPER_WARP) : (wide && (warp == SW_NB_WARP));
     const int N = P.N, m = P.m;
     const int G = gridDim.x, cta = blockIdx.x;
     const int baseT = m / G, remT = m % G;
@@ -306,6 +318,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     int *xb = reinterpret_cast<int *>(smem + L.xb);          /* [3][maxT][K]: (32-bit word index << 5) | bit of spin x in a packed row */
     real *us = reinterpret_cast<real *>(smem + L.us);
     real *hs = reinterpret_cast<real *>(smem + L.hs);
+    real *rmx = reinterpret_cast<real *>(smem + L.rmx);      /* FIELD: [TAB][maxT][K] max |J[x][.]| of the attempt's row */
+    real *carry = reinterpret_cast<real *>(smem + L.carry);  /* FIELD: [maxT][K] */
+    real *pend = reinterpret_cast<real *>(smem + L.pend);    /* FIELD: [maxT][32] */
+    unsigned char *cstate = smem + L.cstate;                 /* FIELD: [maxT][8 * sizeof(real)] */
     int *xn = reinterpret_cast<int *>(smem + L.xn);          /* [2 sides][3][K] */
     uint32_t *conf = reinterpret_cast<uint32_t *>(smem + L.conf);       /* [2 buffers][2 sides][K] */
     uint32_t *confAny = reinterpret_cast<uint32_t *>(smem + L.confAny); /* [2 buffers][2 sides]: rounds with a non-empty mask */
@@ -353,6 +369,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             }
             us[o] = negLogUniform<real>(p); /* accept iff dE*beta < -ln(u): no exp on the chain's critical path */
             hs[o] = hr[x];
+            if (FIELD) rmx[o] = P.rowMax[x];
         }
         if (remote) {
             for (int idx = t0; idx < 2 * Kw; idx += nthr) {
@@ -491,9 +508,21 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         for (int i = tid; i < n16; i += SW_THREADS) dst[i] = __ldcg(src + i);
     }
     __syncthreads();
-    for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
+    if (!FIELD) for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
     for (int i = tid; i < 2 * NW; i += SW_THREADS) nbsnap[2 * NW + i] = nbsnap[i]; /* windows 0 and 1 both start from S_0 */
-    if (warp == SW_NB_WARP) neighbourWindow(0);
+    if (warp == (FIELD ? (int)SW_FIELD_HELPER_WARP : (int)SW_NB_WARP)) neighbourWindow(0);
+    if (FIELD) { /* per-trotter chain state: phase and local neighbours, frontier (rounds of the step that are final), carries */
+        if (tid < T) {
+            const int gy = gOf(y0 + tid);
+            const int yl = slotOf(gy == 0 ? mRing - 1 : gy - 1), yr = slotOf(gy == mRing - 1 ? 0 : gy + 1);
+            const bool lLocal = (yl >= y0 && yl < y0 + T), rLocal = (yr >= y0 && yr < y0 + T);
+            tinfo[tid] = (uint32_t)sweepPhase(gy, mRing) | ((lLocal ? (uint32_t)(yl - y0 + 1) : 0u) << 2) | ((rLocal ? (uint32_t)(yr - y0 + 1) : 0u) << 8);
+            front[tid] = 0u;
+            uint32_t *cs = reinterpret_cast<uint32_t *>(cstate + (size_t)tid * 8 * sizeof(real));
+            cs[0] = 0u; cs[1] = 0u; cs[2] = 0u; cs[3] = 0u;
+        }
+        for (int i = tid; i < T * K; i += SW_THREADS) carry[i] = real(0);
+    }
 
     /* ---------------- hand-off counters between the warps of this CTA (shared memory, release/acquire at CTA scope) ------
      * There is no CTA-wide barrier inside the sweep: every warp runs its own loop over the windows and waits only for what it
@@ -635,38 +664,24 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     };
 
     /* ---------------- field mode: what the dot warps do instead of streaming one J row per attempt ----------------
-     * The local fields F[t][j] = sum_i J[j][i] q_t[i] of the owned trotters live in shared memory.  Dot warp d owns the
-     * 128-column groups g = d (mod #dot warps) of every row.  For chain window w it
-     *   1. gathers the <= 2K-1 cross terms J[x][x'] of every attempt straight from global memory (4-byte gathers),
-     *   2. folds the flips ACCEPTED in window w-2 into its columns: F[t][.] -= 2 q_old J[x][.] (J symmetric) -- the only
-     *      full-row traffic left, acceptance-rate x one row per attempt,
-     *   3. hands the chain scaleA (h[x] + 2 F[t][x]) for the attempts of window w whose column it owns.
-     * F then holds exactly the flips of windows <= w-2, i.e. it is the sum against the snapshot S_{w-1} the classic kernel
-     * reduces rows against, so the chain (fold of window w-1, repair with the window's own flips) is unchanged. */
+     * The local fields F[t][j] = sum_i J[j][i] q_t[i] of the owned trotters live in shared memory.  Field warp d owns the
+     * 128-column groups g = d (mod #field warps) of every row.  For chain window w it
+     *   1. folds the flips ACCEPTED in window w-2 into its columns: F[t][.] -= 2 q_old J[x][.] (J symmetric) -- the only
+     *      full-row traffic, acceptance-rate x one row per attempt; the chain warp that accepted the flip has already asked
+     *      L2 for the row (prefetch at commit time, one to two windows earlier),
+     *   2. hands the chain scaleA (h[x] + 2 F[t][x]) for the attempts of window w whose column it owns.
+     * F then holds exactly the flips of windows <= w-2; the chain adds the cross terms J[x'][x] of the flips accepted since
+     * (windows w-1 and w), which it gathers itself when it commits a flip -- 2K four-byte loads per ACCEPTED flip instead
+     * of 2K-1 per attempt. */
     const int nDot = P.dotWarps;
     const int nGroups = FIELD ? (P.ldF >> 7) : 0;
     auto applyFlips = [&](int wf) {
         const int wb = wf & 1, ws = wf & (TAB - 1);
-        /* pass 1: pull this warp's 512-byte segments of every accepted row into L2 (no registers held), so that the
-         * read-modify-write pass below runs at L2 latency instead of one HBM round trip per flip */
-        for (int t = 0; t < T; ++t) {
-            uint32_t bits = accLog[wb * maxT + t];
-            while (bits) {
-                const int rl = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const real *Jrow = Jr + (size_t)xs[(ws * maxT + t) * K + rl] * P.ldJ;
-                const int perGroup = (int)(128 * sizeof(real) / 128); /* 128-byte lines per column group */
-                for (int i = lane; (dw + (i / perGroup) * nDot) < nGroups; i += 32) {
-                    const int g = dw + (i / perGroup) * nDot;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Jrow + (size_t)g * 128 + (size_t)(i % perGroup) * (128 / sizeof(real))));
-                }
-            }
-        }
         for (int t = 0; t < T; ++t) {
             uint32_t bits = accLog[wb * maxT + t];
             const uint32_t sg = sgnLog[wb * maxT + t];
             real *Frow = field + (size_t)t * P.ldF + lane * 4;
-            while (bits) {
+            while (bits) { /* flips in acceptance order: every element sees the same sequence of additions whatever the warp timing */
                 const int rl = __ffs(bits) - 1;
                 bits &= bits - 1;
                 const int x = xs[(ws * maxT + t) * K + rl];
@@ -689,36 +704,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         }
         __syncwarp();
     };
-    auto crossLoad = [&](int w, int e) -> real { /* lane j < K: J[x][x of round j of window w-1]; K <= j < 2K: round j-K of w */
-        const int slot = w & (TAB - 1);
-        const int t = e % T, rl = e / T;
-        int px = -1;
-        if (lane < K) { if (w > 0) px = xs[(((w - 1) & (TAB - 1)) * maxT + t) * K + lane]; }
-        else if (lane < 2 * K && lane - K < rl) px = xs[(slot * maxT + t) * K + (lane - K)];
-        if (px < 0) return real(0);
-        const int x = xs[(slot * maxT + t) * K + rl];
-        return __ldg(Jr + (size_t)x * P.ldJ + px);
-    };
-    auto crossGather = [&](int w) { /* entry e -> warp e % nDot; lane j < 2K picks J[x][x_j]; buffer w & 3 */
-        const int nEnt = T * roundsIn(w), cb = w & 3;
-        for (int e0 = dw; e0 < nEnt; e0 += 8 * nDot) {
-            real cv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * nDot;
-                cv[u] = (e < nEnt) ? crossLoad(w, e) : real(0);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * nDot;
-                if (e < nEnt && lane < 2 * K) cross[((cb * maxT + e % T) * K + e / T) * (2 * K) + lane] = cv[u];
-            }
-        }
-    };
     auto fieldWindow = [&](int w) {
         const int Kw = roundsIn(w), buf = w & 1, slot = w & (TAB - 1);
         const int nEnt = T * Kw;
-        if (w == 0) crossGather(0);
         if (w >= 2) applyFlips(w - 2);
         for (int e = lane; e < nEnt; e += 32) {
             const int t = e % T, rl = e / T;
@@ -726,14 +714,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             const int x = xs[o];
             if ((x >> 7) % nDot == dw) dots[(buf * maxT + t) * K + rl] = P.scaleA * (hs[o] + real(2) * field[(size_t)t * P.ldF + x]);
         }
-        /* one count per dot warp and window (parity buffers): the chain starts window w at nDot * (w / 2 + 1).  The release
-         * also covers the cross terms of window w, gathered at the end of the previous iteration */
+        /* one count per field warp and window (parity buffers): the chain starts window w at nDot * (w / 2 + 1) */
         __syncwarp();
         if (lane == 0) redAddReleaseCta(aRowsDone + 4u * (uint32_t)buf, 1u);
-        if (w + 1 < nW) { /* off the chain's critical path: the cross terms of the NEXT window (they depend on the tables only) */
-            waitCount(aPrepCount, (uint32_t)w + 2u, 20);
-            crossGather(w + 1);
-        }
     };
 
     if (tid == 0) {
@@ -820,7 +803,234 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             prepWindow(wp, lane, 32);
             signalCount(aPrepCount, (uint32_t)wp + 1u);
         }
-    } else if (chainWarp) {
+    } else if (FIELD && chainWarp) {
+        /* ---------------- field mode: the accept chain, one warp per trotter, a whole window evaluated at once ----------------
+         * Chain warp cw owns the trotters t = cw (mod 4).  Lanes 0..K-1 hold the K attempts of the current window of one
+         * trotter, lanes K..2K-1 the attempts of the NEXT window (they only take part in the cross-term gathers).
+         *   evaluate   every attempt at or behind the trotter's frontier is tested against the current spins and fields.  The
+         *              attempts in front of the first "stop" are rejections whose inputs were exact: they are final.
+         *   stop       (a) an accept: committed -- spin flipped, frontier behind it, cross terms J[x'][x_r] of the trotter's later
+         *              attempts of this window and of all attempts of the next one gathered with one asynchronous 4-byte copy
+         *              per lane (cp.async), the row prefetched into L2 for the field warps;
+         *              (b) an attempt that has to wait because an EARLIER attempt of a neighbouring trotter on the same spin
+         *              index is not final yet (rare: same index within a window);
+         *              (c) an attempt whose sign is not certain while the gathers of the last commit are in flight: every
+         *              affected attempt carries the bound 4 scaleA max|J[x'][.]| and is decided only if its margin exceeds it;
+         *              otherwise the warp waits for the copies, applies them and evaluates again.
+         * Only accepted flips serialise, and the HBM latency of their cross terms is hidden behind the attempts that are certain
+         * anyway.  Commit order per trotter is the reference order; attempts of neighbouring trotters on the same spin index are
+         * ordered by the frontier protocol (the later one waits for the earlier one), so the chain is the reference chain exactly.
+         * Trotters of one CTA run on different warps and meet at the end of every window (named barrier 1). */
+        if constexpr (FIELD) {
+        constexpr int CW = SW_FIELD_CHAIN_WARPS;
+        const int cw = warp;
+        const int rI = lane % K, hI = lane / K;
+        const uint32_t rowBytes = (uint32_t)NW * 8u;
+        const uint32_t aMy0 = smemAddr(qcur), aNb = smemAddr(nbsnap), aFront = smemAddr(front), aDots = smemAddr(dots);
+        const uint32_t aPend = smemAddr(pend), aCarry = smemAddr(carry);
+        const int nbPhaseL = sweepPhase(yLeft, mRing), nbPhaseR = sweepPhase(yRight, mRing);
+        const real corrScale = real(-4) * P.scaleA; /* a flip of spin x' changes scaleA (h + 2 sum) of a later attempt on x by -4 scaleA q_old J[x'][x] */
+        const real nbScale2 = real(2) * P.scaleNb;
+        const int rowLines = (int)((size_t)P.ldJ * sizeof(real) / 128);
+        const uint32_t kMask = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
+        unsigned long long nAccepted = 0;
+        auto cst = [&](int t) { return reinterpret_cast<uint32_t *>(cstate + (size_t)t * 8 * sizeof(real)); }; /* [0] pending window + 1, [1] its round, [2] accept bits, [3] sign bits */
+        auto cstR = [&](int t) { return reinterpret_cast<real *>(cstate + (size_t)t * 8 * sizeof(real) + 16); }; /* [0] bound, [1] signed scale of the pending generation */
+
+        for (int w = 0; w < nW; ++w) {
+            const int Kw = roundsIn(w), KwN = (w + 1 < nW) ? roundsIn(w + 1) : 0;
+            const int buf = w & 1, slot = w & (TAB - 1), slotN = (w + 1) & (TAB - 1);
+            const uint32_t wBase = (uint32_t)(w * K);
+            waitCount(aRowsDone + 4u * (uint32_t)buf, (uint32_t)(P.dotWarps * ((w >> 1) + 1)), 0);
+            if (remote) waitCount(aNbCount, (uint32_t)w + 1u, 0);
+            waitCount(aPrepCount, (uint32_t)min(w + 2, nW), 0); /* the gathers of a commit look at the next window's draws */
+            const unsigned long long flagBase = (P.roundBase + (unsigned long long)w * K + 1ull) << 1;
+            const long long rrBase = (long long)w * K - K; /* round index of bit 0 of a remote conflict mask */
+            const int fs0 = (w * K) % SW_FLAG_RING;
+            const unsigned long long *nbRowsW = nbsnap + (size_t)buf * 2 * NW;
+
+            /* window start: the corrections carried over from the previous window, the local conflict masks, the logs */
+            for (int t = cw; t < T; t += CW) {
+                uint32_t *cs = cst(t);
+                if (cs[0] != 0u && cs[0] != (uint32_t)w) { /* a generation issued two windows ago: F has the flip by now */
+                    cpAsyncWaitAll();
+                    __syncwarp();
+                    if (lane == 0) cs[0] = 0u;
+                }
+                if (hI == 0 && rI < Kw) {
+                    const int o = (buf * maxT + t) * K + rI;
+                    dots[o] += carry[t * K + rI];
+                    carry[t * K + rI] = real(0);
+                    if (SQA) {
+                        const uint32_t info = tinfo[t];
+                        const int x = xs[(slot * maxT + t) * K + rI];
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int tn = (int)((info >> (2 + 6 * side)) & 63u) - 1;
+                            uint32_t msk = 0;
+                            if (tn >= 0) {
+                                const int *xo = xs + (slot * maxT + tn) * K;
+#pragma unroll
+                                for (int j = 0; j < K; ++j) msk |= ((j < Kw && xo[j] == x) ? 1u : 0u) << j;
+                            }
+                            lconf[(t * 2 + side) * K + rI] = msk;
+                        }
+                    }
+                }
+                if (lane == 0) { cs[2] = 0u; cs[3] = 0u; }
+            }
+            __syncwarp();
+
+            for (;;) {
+                bool allDone = true, progress = false;
+                for (int t = cw; t < T; t += CW) {
+                    const uint32_t fr = front[t] - wBase; /* rounds of this window that are final (only this warp writes it) */
+                    if (fr >= (uint32_t)Kw) continue;
+                    allDone = false;
+                    uint32_t *cs = cst(t);
+                    const uint32_t pw = cs[0], pr0 = cs[1];
+                    const real pB = cstR(t)[0];
+                    const uint32_t info = tinfo[t];
+                    const int o = (slot * maxT + t) * K + rI;
+                    const bool valid = (hI == 0) && (rI < Kw) && ((uint32_t)rI >= fr);
+                    bool stop = false, blk = false, unc = false;
+                    uint32_t up = 0, wv = 0, aw = 0, bit = 0;
+                    if (valid) {
+                        const uint32_t xbv = (uint32_t)xb[o];
+                        aw = (xbv >> 5) << 2; bit = xbv & 31u;
+                        wv = ldsU32(aMy0 + (uint32_t)t * rowBytes + aw);
+                        up = (wv >> bit) & 1u;
+                        real vv;
+                        ldsReal(aDots + (uint32_t)(((buf * maxT + t) * K + rI) * sizeof(real)), vv);
+                        if (SQA) {
+                            const int ph = (int)(info & 3u);
+                            int nb = 0;
+#pragma unroll
+                            for (int side = 0; side < 2; ++side) {
+                                const int tn = (int)((info >> (2 + 6 * side)) & 63u) - 1;
+                                uint32_t nbit;
+                                if (tn >= 0) {
+                                    const uint32_t lm = lconf[(t * 2 + side) * K + rI];
+                                    if (lm) { /* rare: the neighbour draws this spin index in this window too */
+                                        const uint32_t need = lm & (((1u << rI) - 1u) | ((((int)(tinfo[tn] & 3u) < ph) ? 1u : 0u) << rI));
+                                        if (need) { /* its earlier attempts on this index must be final: frontier first, spin word after */
+                                            const uint32_t fn = ldAcquireCta(aFront + 4u * (uint32_t)tn) - wBase;
+                                            const uint32_t fin = (fn >= 32u) ? 0xffffffffu : ((1u << fn) - 1u);
+                                            if (need & ~fin) blk = true;
+                                        }
+                                    }
+                                    nbit = (ldsU32(aMy0 + (uint32_t)tn * rowBytes + aw) >> bit) & 1u;
+                                } else {
+                                    nbit = (ldsU32(aNb + (uint32_t)(buf * 2 + side) * rowBytes + aw) >> bit) & 1u;
+                                    const uint32_t cm = conf[(buf * 2 + side) * K + rI];
+                                    if (cm) { /* rare: so does the neighbour owned by another CTA -- its accept flags decide */
+                                        const uint32_t prec = (w > 0 ? kMask : 0u) | (((1u << rI) - 1u) << K) |
+                                                              ((((side ? nbPhaseR : nbPhaseL) < ph) ? 1u : 0u) << (K + rI));
+                                        if (cm & prec) {
+                                            const int rb = remoteBitTry(nbRowsW + (size_t)side * NW, xs[o], cm & prec, rrBase, P.roundBase,
+                                                                        aFlags + (size_t)(side ? slotR : slotL) * SW_FLAG_RING, 0);
+                                            if (rb < 0) blk = true; else nbit = (uint32_t)rb;
+                                        }
+                                    }
+                                }
+                                nb += (int)nbit;
+                            }
+                            vv -= nbScale2 * real(nb - 1);
+                        }
+                        if (!blk) {
+                            const real sv = up ? vv : -vv, lnu = us[o];
+                            /* gathers in flight change vv by at most pB: issued this window -> the rounds after the commit,
+                             * issued in the previous window -> every round */
+                            const bool affected = (pw != 0u) && (pw != (uint32_t)w + 1u || (uint32_t)rI > pr0);
+                            if (affected && fabs(sv - lnu) <= pB + real(1e-5) * fabs(sv)) unc = true;
+                            else stop = sv < lnu; /* exp(-dE beta) > u */
+                        }
+                    }
+                    const uint32_t stopBits = __ballot_sync(0xffffffffu, stop || blk || unc) & kMask;
+                    const uint32_t blkBits = __ballot_sync(0xffffffffu, blk), uncBits = __ballot_sync(0xffffffffu, unc);
+                    const uint32_t upBits = __ballot_sync(0xffffffffu, up != 0u);
+                    const int rs = stopBits ? (__ffs(stopBits) - 1) : Kw;
+                    const bool isBlk = stopBits && ((blkBits >> rs) & 1u), isUnc = stopBits && !isBlk && ((uncBits >> rs) & 1u);
+                    const bool commit = stopBits && !isBlk && !isUnc;
+                    if (pw != 0u && (isUnc || commit)) {
+                        /* the copies of the pending generation must land: lane < K -> later rounds of the window it was issued in,
+                         * lanes K..2K-1 -> the rounds of the window after that one */
+                        cpAsyncWaitAll();
+                        real val;
+                        ldsReal(aPend + (uint32_t)((t * 32 + lane) * sizeof(real)), val);
+                        val *= cstR(t)[1];
+                        if (pw == (uint32_t)w + 1u) {
+                            if (hI == 0 && rI < Kw) dots[(buf * maxT + t) * K + rI] += val;
+                            else if (hI == 1 && rI < KwN) carry[t * K + rI] += val;
+                        } else if (hI == 1 && rI < Kw) dots[(buf * maxT + t) * K + rI] += val;
+                        __syncwarp();
+                        if (lane == 0) cs[0] = 0u;
+                        progress = true;
+                    }
+                    uint32_t newFront = (uint32_t)rs;
+                    if (commit) {
+                        const uint32_t upj = (upBits >> rs) & 1u;
+                        if (lane == rs) stsU32(aMy0 + (uint32_t)t * rowBytes + aw, wv ^ (1u << bit));
+                        const int oS = (slot * maxT + t) * K + rs;
+                        const real *Jrow = Jr + (size_t)xs[oS] * P.ldJ;
+                        int xt = -1;
+                        if (hI == 0) { if (rI > rs && rI < Kw) xt = xs[o]; }
+                        else if (hI == 1) { if (rI < KwN) xt = xs[(slotN * maxT + t) * K + rI]; }
+                        const uint32_t aP = aPend + (uint32_t)((t * 32 + lane) * sizeof(real));
+                        if (xt >= 0) cpAsyncReal(aP, Jrow + xt); else stsReal(aP, real(0));
+                        cpAsyncCommit();
+                        for (int i = lane; i < rowLines; i += 32) prefetchL2(Jrow + (size_t)i * (128 / sizeof(real)));
+                        if (lane == 0) {
+                            cs[0] = (uint32_t)w + 1u; cs[1] = (uint32_t)rs;
+                            cs[2] |= 1u << rs; cs[3] |= upj << rs;
+                            cstR(t)[0] = real(4.004) * P.scaleA * rmx[oS];
+                            cstR(t)[1] = upj ? corrScale : -corrScale;
+                            ++nAccepted;
+                        }
+                        newFront = (uint32_t)rs + 1u;
+                    }
+                    if (lane == 0 && remote && (t == 0 || t == T - 1)) { /* rounds that became final and whose accept flag a neighbouring CTA may read */
+                        uint32_t pmask = ((t == 0 && !((info >> 2) & 63u)) ? pubMask[buf * 2] : 0u) | ((t == T - 1 && !((info >> 8) & 63u)) ? pubMask[buf * 2 + 1] : 0u);
+                        pmask &= ((newFront >= 32u) ? 0xffffffffu : ((1u << newFront) - 1u)) & ~((1u << fr) - 1u);
+                        unsigned long long *myFlags = aFlags + (size_t)(y0 + t) * SW_FLAG_RING;
+                        while (pmask) {
+                            const int r = __ffs(pmask) - 1;
+                            pmask &= pmask - 1;
+                            stRelaxed(myFlags + (fs0 + r) % SW_FLAG_RING, flagBase + (unsigned long long)(2 * r) + ((commit && r == rs) ? 1ull : 0ull));
+                        }
+                    }
+                    __syncwarp(); /* the flipped spin word and the state words are written before the frontier moves */
+                    if (newFront != fr) {
+                        progress = true;
+                        if (lane == 0) stReleaseCta(aFront + 4u * (uint32_t)t, wBase + newFront);
+                    }
+                    __syncwarp();
+                }
+                if (allDone) break;
+                if (!progress) { ++nWaits; __nanosleep(20); } /* everything left waits for another warp or CTA */
+            }
+
+            for (int t = cw; t < T; t += CW) {
+                if (lane == 0) {
+                    const uint32_t accC = cst(t)[2];
+                    accLog[buf * maxT + t] = accC;
+                    sgnLog[buf * maxT + t] = cst(t)[3];
+                    if (remote && (t == 0 || t == T - 1)) /* the neighbouring CTAs rebuild this trotter's spins from the accept bits of the window */
+                        stRelaxed(sBits + ((size_t)(y0 + t) * SW_SNAP_SLOTS + (size_t)(w % SW_SNAP_SLOTS)) * NW,
+                                  ((P.snapBase + (unsigned long long)w + 1ull) << 16) | (unsigned long long)accC);
+                }
+            }
+            __syncwarp();
+            namedBarSync(1, 32 * CW); /* every trotter of the CTA has finished the window */
+            if (cw == 0) signalCount(aReplayDone, (uint32_t)w + 1u);
+        }
+        cpAsyncWaitAll();
+        if (P.stats) {
+            if (lane == 0 && nAccepted) atomicAdd(P.stats, nAccepted);
+            if (lane == 0 && cw == 0) atomicAdd(P.stats + 4, (unsigned long long)waited);
+        }
+        } /* if constexpr (FIELD) */
+    } else if (!FIELD && chainWarp) {
         /* ---------------- the accept chain: lane = trotter ---------------- */
         const bool active = (lane < T);
         const int tl = active ? lane : 0;
@@ -1167,7 +1377,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         if (lane == 0) {
             if (nWaits) atomicAdd(P.stats + 1, nWaits);
             if (dotWarp && dw == 0) atomicAdd(P.stats + 2, (unsigned long long)busy); /* dot warp 0: cycles spent on dot products */
-            if (chainWarp) atomicAdd(P.stats + 3, (unsigned long long)busy);          /* chain warp: cycles spent replaying */
+            if (chainWarp && warp == 0) atomicAdd(P.stats + 3, (unsigned long long)busy); /* chain warp (field mode: the first of four): cycles spent replaying */
             if (snapWarp || nbWarp || allHelperWarp) atomicAdd(P.stats + 5, (unsigned long long)busy); /* snapshot + neighbour (or all-helper) warps */
             if (prepWarp) atomicAdd(P.stats + 6, (unsigned long long)busy);           /* prep warp: Philox tables */
         }
@@ -1203,6 +1413,23 @@ __global__ void ringSpinDotKernel(const signed char *q, int ldq, int N, int m, l
     for (int x = threadIdx.x; x < N; x += blockDim.x) s += (int)a[x] * (int)b[x];
     s = warpSum(s);
     if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)out, (unsigned long long)(long long)s);
+}
+
+/* out[i] = max_j |A[i][j]| -- one warp per row (field mode: bound of a cross term whose gather is still in flight) */
+template <class real> __global__ void rowAbsMaxKernel(real *out, const real *A, int ldA, int rows, int cols) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    real mx = real(0);
+    for (int j = lane; j < cols; j += 32) mx = max(mx, fabs(A[(size_t)row * ldA + j]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) out[row] = mx;
+}
+template <class real> void devRowAbsMax(const B200Device &dev, real *out, const real *A, int ldA, int rows, int cols) {
+    dev.makeCurrent();
+    rowAbsMaxKernel<real><<<(rows + 7) / 8, 256, 0, dev.stream()>>>(out, A, ldA, rows, cols);
+    CUDA_CHECK(cudaGetLastError());
+    ++dev.launchCount;
 }
 
 void launchRandomizeSpin(const B200Device &dev, signed char *q, int ldq, int N, int m, unsigned long long seed,
@@ -1342,6 +1569,7 @@ void B200DenseGraphAnnealer<real>::setHamiltonian(const HostVector &h, const Hos
     sqb_throwErrorIf(dev_ == NULL, "Device not set.");
     clearState(solProblemSet);
     fieldsValid_ = false;
+    if (nProblems_ > 1) { nProblems_ = 1; nReplicas_ = 1; cBatch_.clear(); } /* a problem batch ends here, as in setQUBO() */
     N_ = J.rows;
     m_ = N_ / 4;
     om_ = sq::optMinimize;
@@ -1468,12 +1696,11 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
         sqb_throwErrorIf(sweepModeWanted_ == 1 && (ringWorld_ > 1 || nProblems_ > 1), "field mode cannot be combined with ring sharding or problem batches.");
         if (fieldWanted && ringWorld_ <= 1 && nProblems_ <= 1) {
             for (int k = SW_MAX_K; k >= 4; k >>= 1) {
-                if (forceK ? (k != forceK) : (k > 4 && (size_t)2 * maxT * k * 2 * k * sizeof(real) > (size_t)48 * 1024)) continue;
-                if (SweepSmem<real>(maxT, nw64, 128, 0, k, dotWarps_, ldJ_).total > dev_->smemPerBlockOptin()) continue;
+                if (forceK && k != forceK) continue;
+                if (SweepSmem<real>(maxT, nw64, 128, 0, k, SW_FIELD_WARPS, ldJ_).total > dev_->smemPerBlockOptin()) continue;
                 fieldMode_ = true; K = k; chunkElems = 128; stages = 0;
-                /* the dot warps are lightly loaded in field mode and the accept chain paces the step: chain-critical layout
-                 * (chain alone with the three helper warps on scheduler 0) whatever the number of trotters per CTA */
-                if (!getenv("SQAOD_B200_SWEEP_WIDE")) dotWarps_ = SW_DOT_WARPS;
+                /* field-mode warp layout: four accept-chain warps (one per scheduler), one helper warp, eleven field warps */
+                dotWarps_ = SW_FIELD_WARPS;
                 break;
             }
         }
@@ -1495,6 +1722,8 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     fieldsValid_ = false;
     if (fieldMode_) {
         dF_.alloc(dev_, (size_t)rows * ldJ_);
+        dRowMax_.alloc(dev_, N_);
+        devRowAbsMax<real>(*dev_, dRowMax_.p, dJ_.p, ldJ_, N_, N_);
         dev_->makeCurrent();
         CUDA_CHECK(cudaMemsetAsync(dF_.p, 0, sizeof(real) * (size_t)rows * ldJ_, dev_->stream()));
         /* the tcgen05 GEMM costs ~1 % of a step: refresh every step; the CUDA-core GEMM (fp64) only now and then */
@@ -1637,6 +1866,7 @@ template <class real> void B200DenseGraphAnnealer<real>::makeSolution() {
 template <class real> real B200DenseGraphAnnealer<real>::getSystemE(real G, real beta) const {
     This *self = const_cast<This *>(this);
     sqb_throwErrorIf(nReplicas_ > 1, "getSystemE is defined per solver instance; not available on a replica batch.");
+    sqb_throwErrorIf(ringWorld_ > 1, "getSystemE is not available on a shard of a trotter ring; gather the spins (multigpu.RingShardedDenseAnnealer.get_system_E).");
     self->calculate_E();
     real E = E_.sum() / m_;
     if (sq::isSQAAlgorithm(algo_)) {
@@ -1691,12 +1921,12 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
     P.roundBase = (launchCount_ + 1ull) * (unsigned long long)(N_ + SW_FLAG_RING);
     P.snapBase = (launchCount_ + 1ull) * (unsigned long long)(nWindows_ + 2);
     P.stats = dStats_.p;
-    P.F = NULL; P.ldF = 0; P.writeBackF = 0;
+    P.F = NULL; P.ldF = 0; P.writeBackF = 0; P.rowMax = NULL;
     P.specChain = specChain_ ? 1 : 0;
     if (fieldMode_) {
         if (!fieldsValid_ || stepsSinceRefresh_ >= fieldRefresh_) refreshFields();
         ++stepsSinceRefresh_;
-        P.F = dF_.p; P.ldF = ldJ_;
+        P.F = dF_.p; P.ldF = ldJ_; P.rowMax = dRowMax_.p;
         P.writeBackF = (fieldRefresh_ > 1) ? 1 : 0; /* refreshed before every step otherwise */
         fieldsValid_ = (P.writeBackF != 0);
     }

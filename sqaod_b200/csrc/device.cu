@@ -83,16 +83,16 @@ void B200Device::freePinned(void *p) const {
     if (p) cudaFreeHost(p);
 }
 void B200Device::h2d(void *dst, const void *src, size_t bytes) const {
-    if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_));
+    if (bytes) { makeCurrent(); CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_)); }
 }
 void B200Device::d2h(void *dst, const void *src, size_t bytes) const {
-    if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream_));
+    if (bytes) { makeCurrent(); CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream_)); }
 }
 void B200Device::h2d2D(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height) const {
-    if (width && height) CUDA_CHECK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, stream_));
+    if (width && height) { makeCurrent(); CUDA_CHECK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, stream_)); }
 }
 void B200Device::d2h2D(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height) const {
-    if (width && height) CUDA_CHECK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, stream_));
+    if (width && height) { makeCurrent(); CUDA_CHECK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, stream_)); }
 }
 
 B200Device &asB200(sq::cuda::Device &dev) {

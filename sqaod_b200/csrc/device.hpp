@@ -24,7 +24,9 @@ public:
 
     bool initialized() const { return devNo_ >= 0; }
     void makeCurrent() const;
-    cudaStream_t stream() const { return stream_; }
+    /* the stream every kernel of this Device is launched on; selects the device first, so that solvers assigned to
+     * different devices can be interleaved in one process (every launch site evaluates dev.stream()) */
+    cudaStream_t stream() const { makeCurrent(); return stream_; }
     /* bench.py / torch interop: run on a caller-provided stream (e.g. torch's current stream). */
     void setExternalStream(cudaStream_t s);
     void synchronize() const;

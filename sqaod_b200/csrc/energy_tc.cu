@@ -258,10 +258,12 @@ void tcSpinGemmBf16(const B200Device &dev, float *d_C, int ldc, const TcOperand 
     const int mPad = sq::roundUp(m, TC_BM);
     CUtensorMap mapQ;
     makeMap(&mapQ, const_cast<unsigned short *>(d_Qbf), mPad, B.Kp, TC_BM);
-    static bool attrSet = false;
-    if (!attrSet) {
+    static unsigned long long attrSetMask = 0ull; /* the attribute is per device: one bit per device number */
+    dev.makeCurrent();
+    const unsigned long long devBit = 1ull << (dev.devNo() & 63);
+    if (!(attrSetMask & devBit)) {
         CUDA_CHECK(cudaFuncSetAttribute(tcSpinGemmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-        attrSet = true;
+        attrSetMask |= devBit;
     }
     dim3 grid((m + TC_BM - 1) / TC_BM, (B.rows + TC_BN - 1) / TC_BN);
     tcSpinGemmKernel<<<grid, TC_THREADS, TC_SMEM_BYTES, dev.stream()>>>(mapQ, *(const CUtensorMap *)B.map, d_C, ldc, m, B.rows, B.rowsPad,

@@ -87,6 +87,16 @@ __device__ __forceinline__ void stReleaseCta(uint32_t a, uint32_t v) { asm volat
 __device__ __forceinline__ void redAddReleaseCta(uint32_t a, uint32_t v) {
     asm volatile("red.release.cta.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+/* per-thread asynchronous 4- / 8-byte copies global -> shared (SASS: LDGSTS); waitAll covers every copy this thread issued */
+__device__ __forceinline__ void cpAsyncReal(uint32_t dst, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpAsyncReal(uint32_t dst, const double *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 /* named barrier over `count` threads (a multiple of 32) of the CTA; warps may arrive from different code paths */
 __device__ __forceinline__ void namedBarSync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 

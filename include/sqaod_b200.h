@@ -88,6 +88,11 @@ int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, 
  * [3] chain-warp busy cycles, [5] helper-warp busy cycles (snapshots, conflict masks), [6] prep-warp busy cycles (Philox
  * tables), [4] / [7] chain-warp cycles waiting for dot products / for neighbour data */
 int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int dtype);
+/* the eight counters above plus the field-mode chain profile of chain warp 0, summed over CTAs: [8] cycles waiting for
+ * cross-term gathers, [9] cycles idle (blocked on another warp / CTA), [10] cycles in the per-window barrier of the chain warps,
+ * [11] evaluation passes, [12] / [13] gather waits forced by an uncertain attempt / by a second commit, [14] passes that
+ * ended on a blocked attempt */
+int sqb_dg_annealer_get_profile(sqb_handle ann, unsigned long long *out16, int dtype);
 /* how annealOneStep obtains h_x + sum_j J_xj q_j (no reference counterpart; both modes run the same Markov chain):
  *   0 "classic": one J row streamed per attempt (N*sizeof(real) bytes of traffic per attempt);
  *   1 "field":   the local fields of every trotter are computed once per step (J.q spin GEMM, tensor cores for fp32), kept in

@@ -320,6 +320,12 @@ class BipartiteGraphAnnealer(object):
         r = _creal(self.dtype)
         return self.dtype(_fn('orc_bga_system_E', self.dtype)(self._o, r(G), r(beta)))
 
+    def stats(self):
+        """(accepted flips, accept tests that sat within a rounding error of the threshold)"""
+        a = C.c_longlong(0); b = C.c_longlong(0)
+        _fn('orc_bga_stats', self.dtype)(self._o, C.byref(a), C.byref(b))
+        return a.value, b.value
+
 
 # ---------------------------------------------------------------- brute force
 def dense_graph_bf_search(W, optimize=0, dtype=np.float64, tile_size=1024, x_begin=0, x_end=None):

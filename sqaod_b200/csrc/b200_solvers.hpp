@@ -74,6 +74,7 @@ public:
     void getStats(unsigned long long *accepted, unsigned long long *waits) const;
     void getBarrierStats(unsigned long long *dot, unsigned long long *chain) const { *dot = lastBarrierWaitDot_; *chain = lastBarrierWaitChain_; }
     void getCounters(unsigned long long out[8]) const; /* raw sweep counters, see SweepParams::stats */
+    void getProfile(unsigned long long out[16]) const; /* counters + the field-mode chain profile (stats[8..15]) */
     int numTrotters() const { return m_; }
     /* replica batch: R independent replicas of the problem (seed + r) annealed side by side; spin / energy rows are [r][y] */
     void setNumReplicas(int n);
@@ -118,7 +119,9 @@ private:
     bool fieldMode_ = false;
     bool specChain_ = true;        /* window-parallel accept chain (SQAOD_B200_SWEEP_SPEC=0: the sequential per-round chain) */
     DevBuf<real> dF_;              /* [m * replicas][ldJ] fields at step start */
-    DevBuf<real> dRowMax_;         /* [N] max_j |J[i][j]| (field mode) */
+    DevBuf<real> dRowMax_;         /* scratch of prepare(): max_j |J[i][j]| per row */
+    real jAbsMax_ = real(0);       /* max |J| (field mode: bound of a cross term in flight) */
+    bool fieldsHaveH_ = false;     /* dF_ holds h + 2 J.q (written back by a sweep) instead of the spin GEMM's J.q */
     bool fieldsValid_ = false;     /* dF_ matches dq_ (cleared by everything that writes spins or the problem) */
     int fieldRefresh_ = 1, stepsSinceRefresh_ = 0; /* recompute F = J.q with the spin GEMM every fieldRefresh_ steps */
     int sweepModeWanted_ = -1, fieldRefreshWanted_ = 0; /* setSweepMode(); -1 / 0: automatic */

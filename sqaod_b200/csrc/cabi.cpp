@@ -208,6 +208,7 @@ int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, 
     SQB_CATCH
 }
 int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getCounters(out8)) SQB_CATCH }
+int sqb_dg_annealer_get_profile(sqb_handle ann, unsigned long long *out16, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getProfile(out16)) SQB_CATCH }
 int sqb_dg_annealer_set_sweep_mode(sqb_handle ann, int mode, int field_refresh, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->setSweepMode(mode, field_refresh)) SQB_CATCH }
 int sqb_dg_annealer_get_sweep_mode(sqb_handle ann, int *mode, int dtype) { SQB_TRY DISPATCH(dtype, *mode = DGAX(real)->fieldMode() ? 1 : 0) SQB_CATCH }
 int sqb_dg_annealer_get_spins(sqb_handle ann, signed char *q, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getSpinsRaw(q)) SQB_CATCH }

@@ -99,14 +99,15 @@ template <class real> struct SweepParams {
      * step start (spin GEMM or the previous step's write-back); kept in shared memory and updated incrementally by the sweep */
     real *F;
     int ldF, writeBackF;
-    const real *rowMax; /* field mode: max_j |J[i][j]| per row -- bounds a cross term whose gather is still in flight */
+    real uncBound;   /* field mode: 4 scaleA max|J| (with slack) -- bounds the cross term of a gather that is still in flight */
+    int fieldHasH;   /* field mode: the rows in F already hold h + 2 J.q (written back by the previous step) instead of J.q */
     int specChain; /* accept chain evaluates a whole window in parallel and commits flips in order (see the chain warp) */
     unsigned long long *stats;       /* [0] accepted flips, [1] remote wait polls, [2]/[3] busy cycles of dot warp 0 / the chain warp, summed over CTAs */
 };
 
 /* shared-memory carve-up, identical on host and device */
 template <class real> struct SweepSmem {
-    size_t field, ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, rmx, xn, conf, confAny, accLog, sgnLog, spec, carry, pend, cstate, counter, total;
+    size_t field, ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, confAny, accLog, sgnLog, spec, carry, pend, cstate, counter, total;
     /* fieldElems > 0: field mode -- T rows of fieldElems local fields instead of the TMA ring (stages == 0) */
     __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K, int dotWarps, int fieldElems = 0) {
         size_t o = 0;
@@ -124,8 +125,7 @@ template <class real> struct SweepSmem {
         xb = o; o += tab * T * K * 4;
         o = (o + 15) & ~(size_t)15;
         us = o; o += tab * T * K * sizeof(real);
-        hs = o; o += tab * T * K * sizeof(real);
-        rmx = o; o += (fieldElems ? tab : 0) * T * K * sizeof(real);
+        hs = o; o += (fieldElems ? 0 : tab) * T * K * sizeof(real); /* field mode keeps h inside its field rows */
         xn = o; o += (size_t)2 * tab * K * 4;
         conf = o; o += (size_t)2 * 2 * K * 4;
         confAny = o; o += 32; /* + pubMask[2 buffers][2 sides] */
@@ -318,7 +318,6 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     int *xb = reinterpret_cast<int *>(smem + L.xb);          /* [3][maxT][K]: (32-bit word index << 5) | bit of spin x in a packed row */
     real *us = reinterpret_cast<real *>(smem + L.us);
     real *hs = reinterpret_cast<real *>(smem + L.hs);
-    real *rmx = reinterpret_cast<real *>(smem + L.rmx);      /* FIELD: [TAB][maxT][K] max |J[x][.]| of the attempt's row */
     real *carry = reinterpret_cast<real *>(smem + L.carry);  /* FIELD: [maxT][K] */
     real *pend = reinterpret_cast<real *>(smem + L.pend);    /* FIELD: [maxT][32] */
     unsigned char *cstate = smem + L.cstate;                 /* FIELD: [maxT][8 * sizeof(real)] */
@@ -368,8 +367,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 xb[o] = ((2 * w64 + (bit >> 5)) << 5) | (bit & 31);
             }
             us[o] = negLogUniform<real>(p); /* accept iff dE*beta < -ln(u): no exp on the chain's critical path */
-            hs[o] = hr[x];
-            if (FIELD) rmx[o] = P.rowMax[x];
+            if (!FIELD) hs[o] = hr[x]; /* field mode keeps h inside its field rows */
         }
         if (remote) {
             for (int idx = t0; idx < 2 * Kw; idx += nthr) {
@@ -501,11 +499,18 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     prepWindow(2, tid, SW_THREADS);
     if (FIELD) prepWindow(3, tid, SW_THREADS);
     real *const Fg = FIELD ? P.F + ((size_t)replica * m + y0) * P.ldF : NULL; /* this CTA's rows of the field matrix */
-    if (FIELD) { /* ldF is a multiple of 128 elements: 16-byte copies */
-        const int n16 = (int)((size_t)T * P.ldF * sizeof(real) / 16);
-        const int4 *src = reinterpret_cast<const int4 *>(Fg);
-        int4 *dst = reinterpret_cast<int4 *>(field);
-        for (int i = tid; i < n16; i += SW_THREADS) dst[i] = __ldcg(src + i);
+    if (FIELD) { /* the field rows in shared memory hold H[t][j] = h[j] + 2 sum_i J[j][i] q_t[i]; ldF is a multiple of 128 elements */
+        if (P.fieldHasH) {
+            const int n16 = (int)((size_t)T * P.ldF * sizeof(real) / 16);
+            const int4 *src = reinterpret_cast<const int4 *>(Fg);
+            int4 *dst = reinterpret_cast<int4 *>(field);
+            for (int i = tid; i < n16; i += SW_THREADS) dst[i] = __ldcg(src + i);
+        } else {
+            for (int i = tid; i < T * P.ldF; i += SW_THREADS) {
+                const int j = i % P.ldF;
+                field[i] = (j < N ? hr[j] : real(0)) + real(2) * __ldcg(Fg + i);
+            }
+        }
     }
     __syncthreads();
     if (!FIELD) for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
@@ -536,14 +541,16 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
      * replayed, one full window before the chain needs them. */
     const uint32_t aSync = smemAddr(taskCounter);
     const uint32_t aRowsDone = aSync + 4, aReplayDone = aSync + 12, aSnapCount = aSync + 16, aNbCount = aSync + 20, aPrepCount = aSync + 24;
-    auto waitCount = [&](uint32_t addr, uint32_t want, unsigned ns) { /* whole warp; lane 0 polls, backing off to 16 ns */
+    auto waitCount = [&](uint32_t addr, uint32_t want, unsigned ns) { /* whole warp; lane 0 polls.  ns == 0: latency-critical (accept chain) */
         if (lane == 0 && ldAcquireCta(addr) < want) {
             const long long t0 = clock64();
-            const unsigned nsMax = (ns ? ns : 16u) * 16u;
-            unsigned polls = 0;
+            /* a waiting warp must not eat the issue slots of the warps it waits for (they share its scheduler): sleep between
+             * polls, 32..128 ns for the chain, ns..8 ns for everybody else */
+            const unsigned nsMax = ns ? ns * 8u : 128u;
+            if (!ns) ns = 32u;
             while (ldAcquireCta(addr) < want) {
-                if (ns) { __nanosleep(ns); if (ns < nsMax) ns <<= 1; }
-                else if (++polls >= 16u) ns = 16u; /* a short spin first: the chain's waits are usually a few hundred cycles */
+                __nanosleep(ns);
+                if (ns < nsMax) ns <<= 1;
             }
             waited += clock64() - t0;
         }
@@ -685,7 +692,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 const int rl = __ffs(bits) - 1;
                 bits &= bits - 1;
                 const int x = xs[(ws * maxT + t) * K + rl];
-                const real c = ((sg >> rl) & 1u) ? real(-2) : real(2); /* q_old = +1: the sum loses 2 J */
+                const real c = ((sg >> rl) & 1u) ? real(-4) : real(4); /* q_old = +1: the sum loses 2 J, h + 2 sum loses 4 J */
                 const real *Jrow = Jr + (size_t)x * P.ldJ + lane * 4;
                 for (int g0 = dw; g0 < nGroups; g0 += nDot * 8) {
                     typename RowVec4<real>::type v[8];
@@ -712,7 +719,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             const int t = e % T, rl = e / T;
             const int o = (slot * maxT + t) * K + rl;
             const int x = xs[o];
-            if ((x >> 7) % nDot == dw) dots[(buf * maxT + t) * K + rl] = P.scaleA * (hs[o] + real(2) * field[(size_t)t * P.ldF + x]);
+            if ((x >> 7) % nDot == dw) dots[(buf * maxT + t) * K + rl] = P.scaleA * field[(size_t)t * P.ldF + x];
         }
         /* one count per field warp and window (parity buffers): the chain starts window w at nDot * (w / 2 + 1) */
         __syncwarp();
@@ -834,6 +841,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         const int rowLines = (int)((size_t)P.ldJ * sizeof(real) / 128);
         const uint32_t kMask = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
         unsigned long long nAccepted = 0;
+        /* profile of chain warp 0 (stats[8..15]): cycles in gather waits / idle polls / the window barrier, evaluation passes,
+         * resolves forced by an uncertain attempt / by a second commit, passes that ended on a blocked attempt */
+        long long cycGather = 0, cycIdle = 0, cycBar = 0;
+        unsigned long long nEval = 0, nUncRes = 0, nCommitRes = 0, nBlkStop = 0;
         auto cst = [&](int t) { return reinterpret_cast<uint32_t *>(cstate + (size_t)t * 8 * sizeof(real)); }; /* [0] pending window + 1, [1] its round, [2] accept bits, [3] sign bits */
         auto cstR = [&](int t) { return reinterpret_cast<real *>(cstate + (size_t)t * 8 * sizeof(real) + 16); }; /* [0] bound, [1] signed scale of the pending generation */
 
@@ -952,10 +963,15 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                     const int rs = stopBits ? (__ffs(stopBits) - 1) : Kw;
                     const bool isBlk = stopBits && ((blkBits >> rs) & 1u), isUnc = stopBits && !isBlk && ((uncBits >> rs) & 1u);
                     const bool commit = stopBits && !isBlk && !isUnc;
+                    ++nEval;
+                    if (isBlk) ++nBlkStop;
                     if (pw != 0u && (isUnc || commit)) {
                         /* the copies of the pending generation must land: lane < K -> later rounds of the window it was issued in,
                          * lanes K..2K-1 -> the rounds of the window after that one */
+                        if (isUnc) ++nUncRes; else ++nCommitRes;
+                        const long long tg = clock64();
                         cpAsyncWaitAll();
+                        cycGather += clock64() - tg;
                         real val;
                         ldsReal(aPend + (uint32_t)((t * 32 + lane) * sizeof(real)), val);
                         val *= cstR(t)[1];
@@ -983,7 +999,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                         if (lane == 0) {
                             cs[0] = (uint32_t)w + 1u; cs[1] = (uint32_t)rs;
                             cs[2] |= 1u << rs; cs[3] |= upj << rs;
-                            cstR(t)[0] = real(4.004) * P.scaleA * rmx[oS];
+                            cstR(t)[0] = P.uncBound;
                             cstR(t)[1] = upj ? corrScale : -corrScale;
                             ++nAccepted;
                         }
@@ -1007,7 +1023,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                     __syncwarp();
                 }
                 if (allDone) break;
-                if (!progress) { ++nWaits; __nanosleep(20); } /* everything left waits for another warp or CTA */
+                if (!progress) { /* everything left waits for another warp or CTA */
+                    const long long ti = clock64();
+                    ++nWaits;
+                    __nanosleep(20);
+                    cycIdle += clock64() - ti;
+                }
             }
 
             for (int t = cw; t < T; t += CW) {
@@ -1021,13 +1042,24 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 }
             }
             __syncwarp();
+            const long long tb = clock64();
             namedBarSync(1, 32 * CW); /* every trotter of the CTA has finished the window */
+            cycBar += clock64() - tb;
             if (cw == 0) signalCount(aReplayDone, (uint32_t)w + 1u);
         }
         cpAsyncWaitAll();
         if (P.stats) {
             if (lane == 0 && nAccepted) atomicAdd(P.stats, nAccepted);
-            if (lane == 0 && cw == 0) atomicAdd(P.stats + 4, (unsigned long long)waited);
+            if (lane == 0 && cw == 0) {
+                atomicAdd(P.stats + 4, (unsigned long long)waited);
+                atomicAdd(P.stats + 8, (unsigned long long)cycGather);
+                atomicAdd(P.stats + 9, (unsigned long long)cycIdle);
+                atomicAdd(P.stats + 10, (unsigned long long)cycBar);
+                atomicAdd(P.stats + 11, nEval);
+                atomicAdd(P.stats + 12, nUncRes);
+                atomicAdd(P.stats + 13, nCommitRes);
+                atomicAdd(P.stats + 14, nBlkStop);
+            }
         }
         } /* if constexpr (FIELD) */
     } else if (!FIELD && chainWarp) {
@@ -1722,8 +1754,15 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     fieldsValid_ = false;
     if (fieldMode_) {
         dF_.alloc(dev_, (size_t)rows * ldJ_);
-        dRowMax_.alloc(dev_, N_);
-        devRowAbsMax<real>(*dev_, dRowMax_.p, dJ_.p, ldJ_, N_, N_);
+        { /* max |J|: bounds the cross term of an accepted flip while its gather is in flight */
+            dRowMax_.alloc(dev_, N_);
+            devRowAbsMax<real>(*dev_, dRowMax_.p, dJ_.p, ldJ_, N_, N_);
+            std::vector<real> rm(N_);
+            dev_->d2h(rm.data(), dRowMax_.p, sizeof(real) * N_);
+            dev_->synchronize();
+            jAbsMax_ = *std::max_element(rm.begin(), rm.end());
+            dRowMax_.release();
+        }
         dev_->makeCurrent();
         CUDA_CHECK(cudaMemsetAsync(dF_.p, 0, sizeof(real) * (size_t)rows * ldJ_, dev_->stream()));
         /* the tcgen05 GEMM costs ~1 % of a step: refresh every step; the CUDA-core GEMM (fp64) only now and then */
@@ -1734,7 +1773,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
         if (fieldRefreshWanted_ > 0) fieldRefresh_ = fieldRefreshWanted_;
     }
     allocHandoff();
-    dStats_.alloc(dev_, 8);
+    dStats_.alloc(dev_, 16);
     launchCount_ = 0;
     CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(true, K_, fieldMode_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
     CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(false, K_, fieldMode_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
@@ -1921,12 +1960,15 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
     P.roundBase = (launchCount_ + 1ull) * (unsigned long long)(N_ + SW_FLAG_RING);
     P.snapBase = (launchCount_ + 1ull) * (unsigned long long)(nWindows_ + 2);
     P.stats = dStats_.p;
-    P.F = NULL; P.ldF = 0; P.writeBackF = 0; P.rowMax = NULL;
+    P.F = NULL; P.ldF = 0; P.writeBackF = 0; P.uncBound = real(0); P.fieldHasH = 0;
     P.specChain = specChain_ ? 1 : 0;
     if (fieldMode_) {
         if (!fieldsValid_ || stepsSinceRefresh_ >= fieldRefresh_) refreshFields();
         ++stepsSinceRefresh_;
-        P.F = dF_.p; P.ldF = ldJ_; P.rowMax = dRowMax_.p;
+        P.F = dF_.p; P.ldF = ldJ_;
+        P.uncBound = real(4.004) * P.scaleA * jAbsMax_;
+        P.fieldHasH = fieldsHaveH_ ? 1 : 0;
+        fieldsHaveH_ = (fieldRefresh_ > 1); /* this step writes h + 2 J.q back */
         P.writeBackF = (fieldRefresh_ > 1) ? 1 : 0; /* refreshed before every step otherwise */
         fieldsValid_ = (P.writeBackF != 0);
     }
@@ -1968,6 +2010,7 @@ template <class real> void B200DenseGraphAnnealer<real>::refreshFields() {
     }
     if (!done) devSpinGemm<real>(*dev_, dF_.p, ldJ_, dJ_.p, ldJ_, dq_.p, ldq_, rows, N_, N_);
     fieldsValid_ = true;
+    fieldsHaveH_ = false; /* raw J.q */
     stepsSinceRefresh_ = 0;
 }
 
@@ -2085,6 +2128,13 @@ template <class real> void B200DenseGraphAnnealer<real>::getCounters(unsigned lo
     for (int i = 0; i < 8; ++i) out[i] = 0;
     if (dStats_.p) {
         dev_->d2h(out, dStats_.p, 8 * sizeof(unsigned long long));
+        dev_->synchronize();
+    }
+}
+template <class real> void B200DenseGraphAnnealer<real>::getProfile(unsigned long long out[16]) const {
+    for (int i = 0; i < 16; ++i) out[i] = 0;
+    if (dStats_.p) {
+        dev_->d2h(out, dStats_.p, 16 * sizeof(unsigned long long));
         dev_->synchronize();
     }
 }

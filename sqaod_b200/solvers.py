@@ -227,9 +227,14 @@ class DenseGraphAnnealer(_SolverBase):
         _lib.check(L.sqb_dg_annealer_get_barrier_cycles(self._cobj, C.byref(d), C.byref(c), self._dt))
         raw = (C.c_ulonglong * 8)()
         _lib.check(L.sqb_dg_annealer_get_counters(self._cobj, raw, self._dt))
+        prof = (C.c_ulonglong * 16)()
+        _lib.check(L.sqb_dg_annealer_get_profile(self._cobj, prof, self._dt))
         return {'accepted': a.value, 'flag_waits': w.value, 'barrier_cycles_dot': d.value, 'barrier_cycles_chain': c.value,
                 'helper_cycles': raw[5], 'prep_cycles': raw[6],
-                'chain_wait_rows_cycles': raw[4], 'chain_wait_neighbour_cycles': raw[7]}
+                'chain_wait_rows_cycles': raw[4], 'chain_wait_neighbour_cycles': raw[7],
+                'chain_gather_wait_cycles': prof[8], 'chain_idle_cycles': prof[9], 'chain_barrier_cycles': prof[10],
+                'chain_eval_passes': prof[11], 'chain_uncertain_resolves': prof[12], 'chain_commit_resolves': prof[13],
+                'chain_blocked_stops': prof[14]}
 
 
 def dense_graph_annealer(W=None, optimize=minimize, dtype=np.float64, device=None, **prefs):

@@ -5,10 +5,18 @@
     python bench.py --impl reference ...                     (the reference's CPU algorithm on the host cores)
 
 metric  = spin-flip attempts per second (BASELINE.json); one step = one annealOneStep = N*m attempts.
-value   = whole-job attempts/s with the problem resident in HBM, timed with CUDA events on the launching stream.
+value   = whole-job attempts/s with the problem resident in HBM, timed with CUDA events on the launching stream, at the
+          reference benchmark's fixed operating point G=0.01, beta=50 (sqaodpy/benchmark/benchmark.py:10-11).
 e2e     = the same metric through the public API (sqaod_b200 -> C ABI) with host buffers: every step uploads the spin
           matrix from pinned memory, anneals one step, evaluates the energies and reads spins + energies back.
-At N > 1 every GPU anneals its own replica of the problem with its own seed ("replicas only"): scaling weak.
+Further legs of the same line (SURVEY.md 8d asks for them because the field-mode sweep's cost follows the acceptance rate):
+  sustained              >= 2 s of back-to-back steps at the fixed point, with its own clock samples
+  config.schedule_sweep  a fresh anneal over the reference example's whole schedule G 5 -> 0.01 (geometric), beta = 50
+                         (sqaodpy/example/dense_graph_annealer.py:60-70), with the acceptance rate per fifth of the schedule
+  classic                the one-J-row-per-attempt kernel (HBM-bound) on the same state
+  comm                   what communicates: brute force N=40 sharded over the ranks + NCCL min/gather merge,
+                         the ring-sharded N=32768 sweep (256 trotters per GPU, NVLink hand-off), 512 replicas per GPU of N=1024 m=128
+At N > 1 every GPU anneals its own replica of the headline problem with its own seed ("replicas only"): scaling weak.
 """
 import argparse
 import json
@@ -78,11 +86,14 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def traffic_from_profile(mode):
-    p = os.path.join(ROOT, 'profiles', 'dense_sweep_ncu_summary.json' if mode == 'classic' else 'r1_field_sweep_ncu_summary.json')
+def ncu_traffic_note(mode):
+    """DRAM bytes per launch of the sweep kernel in the committed ncu capture of THIS round (profiles/), with the acceptance rate it
+    was captured at -- reported next to the live traffic model, never used to compute a number of the line."""
+    p = os.path.join(ROOT, 'profiles', 'r2_classic_sweep_ncu_summary.json' if mode == 'classic' else 'r2_field_sweep_ncu_summary.json')
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get('dram_bytes_per_launch')
+            d = json.load(open(p))
+            return {'dram_bytes_per_launch': d.get('dram_bytes_per_launch'), 'acceptance_rate_at_capture': d.get('acceptance_rate'), 'file': os.path.relpath(p, ROOT)}
         except Exception:
             return None
     return None
@@ -132,6 +143,116 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def device_facts(torch, local_rank, clocks):
+    props = torch.cuda.get_device_properties(local_rank)
+    mhz = (clocks or {}).get('sm_mhz') or props.clock_rate / 1e3
+    return props.multi_processor_count, float(mhz)
+
+
+def timed_steps(torch, stream, ann, Gs, beta, barrier):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for G in Gs:
+        ann.anneal_one_step(G, beta)
+    ev1.record(stream)
+    barrier()
+    return ev0.elapsed_time(ev1)
+
+
+def comm_legs(args, torch, dist, sq, dev, rank, local_rank, world, barrier):
+    """The workloads of SURVEY.md 8e that communicate, at the job's world size (world == 1: the unsharded counterpart)."""
+    import hashlib
+    from sqaod_b200 import multigpu
+    out = {}
+    # ---- C4: dense brute force N = 40, x range sharded over the ranks, one NCCL exchange (all_reduce MIN + all_gather)
+    try:
+        Nbf = args.bf_N
+        rng = np.random.default_rng(40)
+        A = np.rint((rng.random((Nbf, Nbf)) - 0.5) * 16384) / 16384.
+        Wbf = np.asarray(np.triu(A) + np.triu(A, 1).T, np.float32)
+        multigpu.sharded_dense_bf_search(Wbf[:16, :16].copy(), 0, np.float32)           # warm-up (kernels, NCCL)
+        barrier()
+        t0 = time.perf_counter()
+        E, xs = multigpu.sharded_dense_bf_search(Wbf, 0, np.float32)
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        h = hashlib.sha256(np.float64(E).tobytes() + np.asarray(xs, np.int8).tobytes()).hexdigest()[:16]
+        out['bf_n40_sharded'] = {'N': Nbf, 'states': float(1 << Nbf), 'seconds': dt, 'states_per_s': float(1 << Nbf) / dt, 'E_min': float(E),
+                                 'n_argmin': len(xs), 'result_sha16': h,
+                                 'exchange': 'all_reduce(MIN) + all_gather of argmin lists (NCCL)' if world > 1 else 'none (1 rank)'}
+    except Exception as e:
+        out['bf_n40_sharded'] = {'error': str(e)[:300]}
+    # ---- C5a: independent replicas N = 1024, m = 128, 512 per GPU, no data-path collective, final MIN reduce
+    try:
+        Nr, mr, per = 1024, 128, args.replicas_per_gpu
+        Wr = make_problem(Nr, seed=1024)
+        Gs = [5.0 * (0.01 / 5.0) ** (k / 7.0) for k in range(8)]
+        multigpu.anneal_replicas(Wr, world, Gs[:2], BETA, np.float32, n_trotters=mr)     # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        best, _, _, _ = multigpu.anneal_replicas(Wr, per * world, Gs, BETA, np.float32, n_trotters=mr)
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        out['replicas_c5a'] = {'N': Nr, 'm': mr, 'replicas': per * world, 'steps_per_replica': len(Gs), 'seconds': dt,
+                               'attempts_per_s': float(per * world) * len(Gs) * Nr * mr / dt, 'best_E': float(best),
+                               'note': 'wall clock incl. prepare / randomize / get_E; J resident per GPU; final all_reduce(MIN)'}
+    except Exception as e:
+        out['replicas_c5a'] = {'error': str(e)[:300]}
+    # ---- C5b: ONE instance N = 32768, trotter ring sharded over the ranks (256 trotters per GPU), NVLink P2P hand-off
+    try:
+        Nq, per_m, steps = args.ring_N, 256, 3
+        if world > 1:
+            ring = multigpu.RingShardedDenseAnnealer(('random', Nq, 32768), 0, np.float32, n_trotters=per_m * world)
+            ring.seed(7); ring.prepare(); ring.randomize_spin()
+            ann = ring.ann
+            step = ring.anneal_one_step
+        else:
+            ann = sq.dense_graph_annealer(None, sq.minimize, np.float32, device=dev)
+            ann.set_qubo_random(Nq, 32768)
+            ann.set_preferences(n_trotters=per_m)
+            ann.seed(7); ann.prepare(); ann.randomize_spin()
+            step = ann.anneal_one_step
+        step(G_FIXED, BETA)
+        barrier()
+        s0 = ann.get_stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(torch.cuda.current_stream())
+        for _ in range(steps):
+            step(G_FIXED, BETA)
+        ev1.record(torch.cuda.current_stream())
+        barrier()
+        ms = ev0.elapsed_time(ev1) / steps
+        s1 = ann.get_stats()
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+        sms, mhz = device_facts(torch, local_rank, None)
+        wait_ms = (s1['chain_wait_neighbour_cycles'] - s0['chain_wait_neighbour_cycles']) / float(min(sms, per_m)) / (mhz * 1e3) / steps
+        out['ring_c5b'] = {'N': Nq, 'm': per_m * world, 'trotters_per_gpu': per_m, 'ms_per_step': ms_max,
+                           'attempts_per_s': float(Nq) * per_m * world / (ms_max * 1e-3), 'sweep_mode': ann.get_sweep_mode(),
+                           'neighbour_wait_ms_per_step_per_cta': wait_ms, 'neighbour_wait_frac': wait_ms / ms_max,
+                           'flag_polls_per_step': (s1['flag_waits'] - s0['flag_waits']) / steps,
+                           'exchange': ('accept words + conflict flags + per-sweep edge-trotter push over NVLink (CUDA IPC peer memory), no NCCL in the data path'
+                                        if world > 1 else 'none (1 rank: the whole ring on one GPU)')}
+        del ann
+    except Exception as e:
+        out['ring_c5b'] = {'error': str(e)[:300]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -144,7 +265,17 @@ def main():
     ap.add_argument('--sweep-mode', default='auto', choices=['auto', 'classic', 'field'],
                     help="how the sweep gets its local fields: 'classic' streams one J row per attempt, 'field' keeps J.q in shared "
                          "memory and streams one row per accepted flip (same Markov chain); 'auto' = the library's choice")
+    ap.add_argument('--sustain-seconds', type=float, default=2.5, help='length of the sustained leg (0: skip)')
+    ap.add_argument('--schedule-steps', type=int, default=100, help='steps of the G 5 -> 0.01 schedule leg (0: skip)')
+    ap.add_argument('--no-classic-leg', action='store_true')
+    ap.add_argument('--no-comm-legs', action='store_true', help='skip the brute-force / ring / replica legs')
+    ap.add_argument('--bf-N', type=int, default=40)
+    ap.add_argument('--ring-N', type=int, default=32768)
+    ap.add_argument('--replicas-per-gpu', type=int, default=512)
+    ap.add_argument('--quick', action='store_true', help='headline + e2e legs only')
     args = ap.parse_args()
+    if args.quick:
+        args.sustain_seconds, args.schedule_steps, args.no_classic_leg, args.no_comm_legs, args.no_cpu_baseline = 0.0, 0, True, True, True
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -181,7 +312,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident throughput ----------------
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    attempts_per_step = N * m
+
+    # ---------------- headline: device-resident throughput at the fixed operating point ----------------
     for _ in range(args.warmup):
         ann.anneal_one_step(G_FIXED, BETA)
     barrier()
@@ -190,22 +329,11 @@ def main():
         sampler.start()
     dev.launch_count(reset=True)
     stats0 = ann.get_stats()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        ann.anneal_one_step(G_FIXED, BETA)
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms = timed_steps(torch, stream, ann, [G_FIXED] * args.steps, BETA, barrier)
     launches = dev.launch_count()
     stats1 = ann.get_stats()
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    attempts_per_step = N * m
+    ms_max = max_over_ranks(ms)
     value = world * attempts_per_step * args.steps / (ms_max * 1e-3)
 
     # ---------------- end to end through the public API with host buffers ----------------
@@ -220,51 +348,124 @@ def main():
         E = ann.get_E()                         # energy kernel + D2H of m reals
         ann.get_spins(out=q_host)               # D2H of the spin matrix into the pinned buffer
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * attempts_per_step * e2e_steps / float(t.item())
+    e2e_value = world * attempts_per_step * e2e_steps / max_over_ranks(time.perf_counter() - t0)
+
+    # ---------------- sustained: >= 2 s back to back, own clock samples (power-cap behaviour on record) ----------------
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = int(max(args.steps, np.ceil(args.sustain_seconds * 1e3 / (ms / args.steps))))
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        ms_sus = timed_steps(torch, stream, ann, [G_FIXED] * n_sus, BETA, barrier)
+        clocks2 = sampler2.stop() if rank == 0 else None
+        ms_sus_max = max_over_ranks(ms_sus)
+        sustained = {'steps': n_sus, 'seconds': ms_sus_max * 1e-3, 'ms_per_step': ms_sus_max / n_sus,
+                     'value': world * attempts_per_step * n_sus / (ms_sus_max * 1e-3), 'unit': 'attempts/s', 'clocks': clocks2}
+
+    # ---------------- the whole annealing schedule: G 5 -> 0.01 geometric, beta = 50, from random spins ----------------
+    schedule = None
+    if args.schedule_steps > 0:
+        S = args.schedule_steps
+        Gs = [5.0 * (0.01 / 5.0) ** (k / float(S - 1)) for k in range(S)]
+        ann.randomize_spin()
+        parts, tot_ms, tot_acc = [], 0.0, 0
+        n_part = 5
+        for i in range(n_part):
+            chunk = Gs[i * S // n_part:(i + 1) * S // n_part]
+            a0 = ann.get_stats()['accepted']
+            ms_c = max_over_ranks(timed_steps(torch, stream, ann, chunk, BETA, barrier))
+            acc = ann.get_stats()['accepted'] - a0
+            parts.append({'G_from': chunk[0], 'G_to': chunk[-1], 'steps': len(chunk), 'ms_per_step': ms_c / len(chunk),
+                          'acceptance_rate': acc / float(attempts_per_step * len(chunk))})
+            tot_ms += ms_c
+            tot_acc += acc
+        schedule = {'protocol': 'randomize_spin, then G = 5 -> 0.01 geometric over %d steps at beta = 50 (the range of '
+                                'sqaodpy/example/dense_graph_annealer.py:60-70)' % S,
+                    'steps': S, 'ms_per_step': tot_ms / S, 'value': world * attempts_per_step * S / (tot_ms * 1e-3), 'unit': 'attempts/s',
+                    'acceptance_rate': tot_acc / float(attempts_per_step * S), 'by_fifth': parts, 'E_min_final': float(np.min(ann.get_E()))}
+
+    # ---------------- the classic (one J row per attempt, HBM-bound) kernel on the equilibrated state ----------------
+    classic = None
+    if not args.no_classic_leg and mode != 'classic':
+        q_now = ann.get_spins()
+        ann_c = sq.dense_graph_annealer(W, sq.minimize, np.float32, n_trotters=m, device=dev)
+        ann_c.seed(1000 + rank)
+        ann_c.set_sweep_mode('classic')
+        ann_c.prepare()
+        ann_c.set_qset(q_now)
+        for _ in range(2):
+            ann_c.anneal_one_step(G_FIXED, BETA)
+        n_c = 6
+        c0 = ann_c.get_stats()['accepted']
+        ms_c = max_over_ranks(timed_steps(torch, stream, ann_c, [G_FIXED] * n_c, BETA, barrier))
+        acc_c = ann_c.get_stats()['accepted'] - c0
+        classic = {'ms_per_step': ms_c / n_c, 'value': world * attempts_per_step * n_c / (ms_c * 1e-3), 'unit': 'attempts/s', 'steps': n_c,
+                   'acceptance_rate': acc_c / float(attempts_per_step * n_c), 'kernel': 'denseSweepKernel<float,true,16,false>',
+                   'algorithmic_bytes_per_launch': attempts_per_step * N * 4}
+        del ann_c
+
+    comm = None
+    if not args.no_comm_legs:
+        comm = comm_legs(args, torch, dist, sq, dev, rank, local_rank, world, barrier)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
+        sms, mhz = device_facts(torch, local_rank, clocks)
+        ctas = min(sms, m)
+        step_s = ms / args.steps * 1e-3
         algo_bytes = attempts_per_step * N * 4          # one J row per attempt
-        achieved = algo_bytes / (ms / args.steps * 1e-3) / 1e9
         accepted = stats1['accepted'] - stats0['accepted']
-        traffic = traffic_from_profile(mode) if (N == N_SPINS and m == M_TROTTERS) else None
+        acc_rate = accepted / float(attempts_per_step * args.steps)
+        cyc_ms = lambda key: (stats1[key] - stats0[key]) / float(ctas) / (mhz * 1e3) / args.steps
+        if mode == 'field':
+            # bytes the field-mode sweep has to move per launch, from this run's counters: one J row + 2K 32-byte sectors of cross
+            # terms per ACCEPTED flip, the field rows in (once per step), spins in and out.  L2 hits on J can only lower it.
+            traffic = (accepted / float(args.steps)) * (N * 4 + 32 * 32) + m * N * 4 + 2 * m * N
+            bound = 'latency (accept chain + per-window hand-offs between the warps and CTAs), not HBM'
+            traffic_src = 'live model from this run: accepted flips x (J row + cross-term sectors) + field rows + spins'
+        else:
+            traffic = float(algo_bytes)
+            bound = 'hbm'
+            traffic_src = 'one J row per attempt (L2 hits lower the DRAM share)'
+        roofline = {'bound': bound, 'achieved': traffic / step_s / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': traffic / step_s / 1e9 / peak,
+                    'traffic': traffic, 'traffic_source': traffic_src, 'traffic_ncu': ncu_traffic_note(mode), 'peak_source': peak_src,
+                    'kernel': 'denseSweepKernel<float,true,16,%s>' % ('true' if mode == 'field' else 'false'),
+                    'algorithmic_bytes_per_launch': algo_bytes, 'algorithmic_GBps': algo_bytes / step_s / 1e9,
+                    'algorithmic_speedup': algo_bytes / step_s / 1e9 / peak,
+                    'note': 'achieved/frac: bytes the kernel moves per launch / launch time / measured copy peak.  algorithmic_*: the SURVEY 8d '
+                            'figure (one J row per attempt); in field mode rows of rejected attempts are never fetched, so algorithmic_speedup '
+                            '> 1 is an algorithmic gain, not bandwidth'}
+        if classic:
+            cs = classic['ms_per_step'] * 1e-3
+            classic['roofline'] = {'bound': 'hbm', 'achieved': algo_bytes / cs / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': algo_bytes / cs / 1e9 / peak,
+                                   'note': 'algorithmic bytes (one row per attempt) / time; the share that misses L2 is in profiles/ (ncu)',
+                                   'traffic_ncu': ncu_traffic_note('classic')}
         line = {
             'metric': 'spin-flip attempts/sec (dense SQA N=8192 m=512)', 'value': value, 'unit': 'attempts/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'dense-graph SQA N=%d m=%d fp32 random QUBO (BASELINE.json configs[1]); one independent '
                                    'replica per GPU' % (N, m), 'G': G_FIXED, 'beta': BETA, 'algorithm': 'coloring',
-                       'sweep_mode': mode + (' (local fields J.q recomputed on the tensor cores every step, kept in shared memory, one J row '
-                                             'streamed per ACCEPTED flip)' if mode == 'field' else ' (one J row streamed per attempt)'),
+                       'sweep_mode': mode + (' (local fields h + 2 J.q from the tensor-core spin GEMM every step, kept in shared memory, one J row '
+                                             'streamed per ACCEPTED flip; one accept-chain warp per trotter)' if mode == 'field' else ' (one J row streamed per attempt)'),
                        'l2': 'J is %d MiB > 126 MB L2 and rows are drawn at random, no flush needed' % (N * N * 4 >> 20),
-                       'acceptance_rate': accepted / float(attempts_per_step * args.steps),
+                       'acceptance_rate': acc_rate,
                        'flag_waits': stats1['flag_waits'] - stats0['flag_waits'],
-                       'busy_ms_per_step_per_cta': {k: (stats1['barrier_cycles_' + k] - stats0['barrier_cycles_' + k]) / 148.0 / 1.965e6 / args.steps
-                                               for k in ('dot', 'chain')},
-                       # of the chain warp's time: waiting for the local fields of the next window / for the neighbouring CTAs' data
-                       'chain_wait_ms_per_step_per_cta': {k: (stats1['chain_wait_%s_cycles' % k] - stats0['chain_wait_%s_cycles' % k]) / 148.0 / 1.965e6 / args.steps
-                                                          for k in ('rows', 'neighbour')}},
+                       'device': {'sms': sms, 'sm_mhz_used_for_cycle_conversion': mhz},
+                       # chain warp 0 and field warp 0 of every CTA, averaged: where a step goes
+                       'ms_per_step_per_cta': {'chain_busy': cyc_ms('barrier_cycles_chain'), 'chain_wait_fields': cyc_ms('chain_wait_rows_cycles'),
+                                               'chain_wait_neighbour_ctas': cyc_ms('chain_wait_neighbour_cycles'),
+                                               'field_warp_busy': cyc_ms('barrier_cycles_dot')},
+                       'schedule_sweep': schedule},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'attempts/s', 'h2d_bytes_per_step': m * N, 'd2h_bytes_per_step': m * N + m * 4,
                     'steps': e2e_steps, 'E_min': float(np.min(E))},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'peak_source': peak_src,
-                         'kernel': 'denseSweepKernel<float,true,16,%s>' % ('true' if mode == 'field' else 'false'),
-                         'algorithmic_bytes_per_launch': algo_bytes,
-                         # the part of the algorithmic bytes that really came from HBM (ncu dram bytes per launch, profiles/):
-                         # frac > 1 on the algorithmic figure is L2 reuse of J rows (classic mode) or rows of rejected attempts
-                         # that were never needed (field mode: incremental local fields), not skipped work
-                         'note': ('field mode is paced by the latency of the accept chain (one warp per CTA, ~430 ns per round), not by HBM: '
-                                  'achieved/frac are the SURVEY 8d algorithmic figure (one J row per attempt, rows of rejected attempts '
-                                  'are never fetched), dram_GBps/dram_frac the bytes the kernel really moves (ncu, profiles/)') if mode == 'field'
-                                 else 'classic mode streams one J row per attempt and is HBM-bound; achieved > dram_GBps is L2 reuse of rows',
-                         'dram_GBps': (traffic / (ms / args.steps * 1e-3) / 1e9) if traffic else None,
-                         'dram_frac': (traffic / (ms / args.steps * 1e-3) / 1e9 / peak) if traffic else None},
+            'roofline': roofline,
+            'sustained': sustained,
+            'classic': classic,
+            'comm': comm,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

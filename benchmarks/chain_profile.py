@@ -28,9 +28,22 @@ ctas, mhz = min(148, a.m), 1.965e6
 ms = lambda c: c / ctas / mhz / a.steps
 nwin = (a.N + 15) // 16
 print('N=%d m=%d mode=%s  %.3f ms/step  acceptance %.4f  windows/step %d' % (a.N, a.m, ann.get_sweep_mode(), dt, d['accepted'] / (a.N * a.m * a.steps), nwin))
-print('chain warp 0 per step per CTA [ms]: busy %.3f (gather waits %.3f, idle polls %.3f, window barrier %.3f) + waiting for fields/tables %.3f'
-      % (ms(d['barrier_cycles_chain']), ms(d['chain_gather_wait_cycles']), ms(d['chain_idle_cycles']), ms(d['chain_barrier_cycles']), ms(d['chain_wait_rows_cycles'])))
+print('chain warp 0 per step per CTA [ms]: busy %.3f (gather waits %.3f, idle polls %.3f, window barrier %.3f) + waiting for fields %.3f / neighbour CTAs %.3f / tables %.3f'
+      % (ms(d['barrier_cycles_chain']), ms(d['chain_gather_wait_cycles']), ms(d['chain_idle_cycles']), ms(d['chain_barrier_cycles']), ms(d['chain_wait_rows_cycles']), ms(d['chain_wait_neighbour_cycles']), ms(d['prep_cycles'])))
+print('chain warps 1-3: window barrier %.3f ms each' % (ms(d['chain_barrier_cycles_others']) / 3))
 print('field warp 0 busy %.3f ms, helper busy %.3f ms' % (ms(d['barrier_cycles_dot']), ms(d['helper_cycles'])))
 pw = lambda c: c / ctas / a.steps / nwin
-print('per CTA and window: eval passes %.2f, uncertain resolves %.3f, second-commit resolves %.3f, blocked stops %.3f, flag/idle polls %.2f'
-      % (pw(d['chain_eval_passes']), pw(d['chain_uncertain_resolves']), pw(d['chain_commit_resolves']), pw(d['chain_blocked_stops']), pw(d['flag_waits'])))
+print('per CTA and window: eval passes %.2f, flag/idle polls %.2f; chain warp 0 segments [ms/step]: window start %.3f, evaluation %.3f, window end %.3f'
+      % (pw(d['chain_eval_passes']), pw(d['flag_waits']), ms(d['chain_uncertain_resolves']), ms(d['chain_commit_resolves']), ms(d['chain_blocked_stops'])))
+
+if ann.get_sweep_mode() == 'field':
+    pc = ann.get_cta_profile().astype(np.float64)
+    t_end = pc[:, 5] - pc[:, 5].min()
+    print('per CTA (last launch): cta T wait_fields[us] wait_nb[us] chain_work[us] loop[us] end[us] accepted passes')
+    for i in list(range(0, len(pc), max(1, len(pc) // 24))) + [len(pc) - 1]:
+        r = pc[i]
+        print('%4d %d %8.1f %8.1f %8.1f %8.1f %8.1f %6d %6d' % (i, r[0], r[1] / mhz * 1e3, r[2] / mhz * 1e3, r[3] / mhz * 1e3, r[4] / mhz * 1e3, t_end[i] / 1e3, r[6], r[7]))
+    for T in sorted(set(pc[:, 0].astype(int))):
+        sel = pc[:, 0] == T
+        print('T=%d: %d CTAs, mean wait_fields %.1f us, wait_nb %.1f us, chain work %.1f us, loop %.1f us' % (
+            T, sel.sum(), pc[sel, 1].mean() / mhz * 1e3, pc[sel, 2].mean() / mhz * 1e3, pc[sel, 3].mean() / mhz * 1e3, pc[sel, 4].mean() / mhz * 1e3))

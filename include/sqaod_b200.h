@@ -93,6 +93,9 @@ int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int d
  * [11] evaluation passes, [12] / [13] gather waits forced by an uncertain attempt / by a second commit, [14] passes that
  * ended on a blocked attempt */
 int sqb_dg_annealer_get_profile(sqb_handle ann, unsigned long long *out16, int dtype);
+/* field mode, last launch, chain warp 0 of every CTA (8 words per CTA): trotters, cycles waiting for fields / for neighbour CTAs,
+ * cycles of chain work, cycles of the whole sweep loop, end time (globaltimer ns), accepted flips of that warp, evaluation passes */
+int sqb_dg_annealer_get_cta_profile(sqb_handle ann, unsigned long long *out, int max_ctas, int *n, int dtype);
 /* how annealOneStep obtains h_x + sum_j J_xj q_j (no reference counterpart; both modes run the same Markov chain):
  *   0 "classic": one J row streamed per attempt (N*sizeof(real) bytes of traffic per attempt);
  *   1 "field":   the local fields of every trotter are computed once per step (J.q spin GEMM, tensor cores for fp32), kept in
@@ -107,6 +110,11 @@ int sqb_dg_annealer_get_sweep_mode(sqb_handle ann, int *mode, int dtype); /* the
 /* a batch of n_problems DIFFERENT QUBOs of the same size (W: n_problems x N x N, row stride ldW elements) annealed side by side
  * in one cooperative launch per step; problem r uses seed + r; spins / energies are returned as n_problems*m rows (SURVEY 8f-2:
  * the caller loop of sqaodpy/sqaod/common/common.py:144-160 run for many problems at once) */
+/* extras for benchmarks and multi-GPU tests: a synthetic symmetric W ~ U(-0.5, 0.5) generated on the device from
+ * Philox(seed, min(i,j), max(i,j)) (optionally on the reference tests' 2^-14 grid), so that large problems (N = 32768: 4 GiB)
+ * need no host generation or upload; get_qubo_random returns the same matrix to the host (for oracle checks) */
+int sqb_dg_annealer_set_qubo_random(sqb_handle ann, int N, unsigned long long seed, int quantize, int optimize, int dtype);
+int sqb_dg_annealer_get_qubo_random(sqb_handle ann, void *W, int N, int ldW, unsigned long long seed, int quantize, int dtype);
 int sqb_dg_annealer_set_qubo_batch(sqb_handle ann, const void *W, int n_problems, int N, int ldW, int optimize, int dtype);
 int sqb_dg_annealer_set_num_replicas(sqb_handle ann, int n_replicas, int dtype);
 int sqb_dg_annealer_get_num_replicas(sqb_handle ann, int *n_replicas, int dtype);

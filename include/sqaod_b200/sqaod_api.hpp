@@ -49,6 +49,9 @@ template <class V> inline V roundUp(V v, int base) { return divru(v, base) * bas
 /* error / log conventions of the reference (common/defines.cpp:12-63): recoverable errors throw
  * std::runtime_error("file:line msg\n"); log() prints iff SQAOD_VERBOSE is set and != '0'. */
 void throwErrorAt(const char *file, unsigned long line, const char *fmt, ...);
+void throwErrorAt(const char *file, unsigned long line);
+void abortAt(const char *file, unsigned long line, const char *fmt, ...);
+void abortAt(const char *file, unsigned long line);
 void log(const char *fmt, ...);
 #define sqb_throwError(...) ::sqaod::throwErrorAt(__FILE__, __LINE__, __VA_ARGS__)
 #define sqb_throwErrorIf(cond, ...) do { if (cond) ::sqaod::throwErrorAt(__FILE__, __LINE__, __VA_ARGS__); } while (0)
@@ -164,6 +167,19 @@ template <class V> bool operator==(const MatrixType<V> &a, const MatrixType<V> &
     if (a.rows != b.rows || a.cols != b.cols) return false;
     for (SizeType r = 0; r < a.rows; ++r) for (SizeType c = 0; c < a.cols; ++c) if (a(r, c) != b(r, c)) return false;
     return true;
+}
+
+/* element-wise conversion into a newly owned container (reference: common/Matrix.h:209-210, 363-365; the pyglue formulas
+ * functions widen 0/1 and +-1 int8 arrays to `real` with it) */
+template <class newV, class V> MatrixType<newV> cast(const MatrixType<V> &mat) {
+    MatrixType<newV> out(mat.rows, mat.cols);
+    for (SizeType r = 0; r < mat.rows; ++r) for (SizeType c = 0; c < mat.cols; ++c) out(r, c) = (newV)mat(r, c);
+    return out;
+}
+template <class newV, class V> VectorType<newV> cast(const VectorType<V> &vec) {
+    VectorType<newV> out(vec.size);
+    for (SizeType i = 0; i < vec.size; ++i) out(i) = (newV)vec(i);
+    return out;
 }
 
 typedef VectorType<char> BitSet;

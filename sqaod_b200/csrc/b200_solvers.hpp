@@ -74,11 +74,15 @@ public:
     void getStats(unsigned long long *accepted, unsigned long long *waits) const;
     void getBarrierStats(unsigned long long *dot, unsigned long long *chain) const { *dot = lastBarrierWaitDot_; *chain = lastBarrierWaitChain_; }
     void getCounters(unsigned long long out[8]) const; /* raw sweep counters, see SweepParams::stats */
-    void getProfile(unsigned long long out[16]) const; /* counters + the field-mode chain profile (stats[8..15]) */
+    void getProfile(unsigned long long out[16]) const;
+    int getCtaProfile(unsigned long long *out, int maxCtas) const; /* per CTA, last launch: [T, wait fields, wait neighbours, chain work, loop cycles, end time (ns), accepted, passes] */ /* counters + the field-mode chain profile (stats[8..15]) */
     int numTrotters() const { return m_; }
     /* replica batch: R independent replicas of the problem (seed + r) annealed side by side; spin / energy rows are [r][y] */
     void setNumReplicas(int n);
     void setQUBOBatch(const real *W, int nProblems, int N, int ldW, sq::OptimizeMethod om);
+    /* synthetic symmetric W ~ U(-0.5, 0.5) generated on the device (benchmarks / multi-GPU tests); getQUBORandom returns the same matrix */
+    void setQUBORandom(int N, unsigned long long seed, bool quantize, sq::OptimizeMethod om);
+    void getQUBORandom(real *W, int N, int ldW, unsigned long long seed, bool quantize) const;
     int numProblems() const { return nProblems_; }
     int numReplicas() const { return nReplicas_; }
     /* ring sharding over several GPUs: this solver anneals trotters [rank*m/world, (rank+1)*m/world) of one ring */
@@ -90,6 +94,7 @@ public:
 
 private:
     void uploadProblem(const real *h, const real *J, int strideJ);
+    void hamiltonianFromDeviceQUBO(const real *dW);
     void prepareTensorCoreOperand();
     void syncBits();
 

@@ -141,6 +141,12 @@ int sqb_dg_annealer_seed(sqb_handle ann, unsigned long long seed, int dtype) { S
 int sqb_dg_annealer_set_qubo(sqb_handle ann, const void *W, int N, int stride, int optimize, int dtype) {
     SQB_TRY DISPATCH(dtype, DGA(real)->setQUBO(mapMat<real>(W, N, N, stride), (sq::OptimizeMethod)optimize)) SQB_CATCH
 }
+int sqb_dg_annealer_set_qubo_random(sqb_handle ann, int N, unsigned long long seed, int quantize, int optimize, int dtype) {
+    SQB_TRY DISPATCH(dtype, DGAX(real)->setQUBORandom(N, seed, quantize != 0, (sq::OptimizeMethod)optimize)) SQB_CATCH
+}
+int sqb_dg_annealer_get_qubo_random(sqb_handle ann, void *W, int N, int ldW, unsigned long long seed, int quantize, int dtype) {
+    SQB_TRY DISPATCH(dtype, DGAX(real)->getQUBORandom((real *)W, N, ldW, seed, quantize != 0)) SQB_CATCH
+}
 int sqb_dg_annealer_set_hamiltonian(sqb_handle ann, const void *h, const void *J, int N, int strideJ, double c, int dtype) {
     SQB_TRY DISPATCH(dtype, DGA(real)->setHamiltonian(mapVec<real>(h, N), mapMat<real>(J, N, N, strideJ), (real)c)) SQB_CATCH
 }
@@ -208,6 +214,7 @@ int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, 
     SQB_CATCH
 }
 int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getCounters(out8)) SQB_CATCH }
+int sqb_dg_annealer_get_cta_profile(sqb_handle ann, unsigned long long *out, int max_ctas, int *n, int dtype) { SQB_TRY DISPATCH(dtype, *n = DGAX(real)->getCtaProfile(out, max_ctas)) SQB_CATCH }
 int sqb_dg_annealer_get_profile(sqb_handle ann, unsigned long long *out16, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getProfile(out16)) SQB_CATCH }
 int sqb_dg_annealer_set_sweep_mode(sqb_handle ann, int mode, int field_refresh, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->setSweepMode(mode, field_refresh)) SQB_CATCH }
 int sqb_dg_annealer_get_sweep_mode(sqb_handle ann, int *mode, int dtype) { SQB_TRY DISPATCH(dtype, *mode = DGAX(real)->fieldMode() ? 1 : 0) SQB_CATCH }

@@ -67,7 +67,7 @@ enum { SW_MAX_K = 16, SW_DOT_WARPS = 12 /* chain-critical layout */, SW_DOT_WARP
        SW_CHAIN_WARP = 0, SW_SNAP_WARP = 4, SW_PREP_WARP = 8, SW_NB_WARP = 12 /* the dot warps are those with warp & 3 != 0 */,
        /* field mode: warps 0-3 are accept-chain warps (one per scheduler, trotter t -> warp t % 4), warp 4 does all the helper
         * work, warps 5-15 own the column groups of the field rows */
-       SW_FIELD_CHAIN_WARPS = 4, SW_FIELD_HELPER_WARP = 4, SW_FIELD_WARPS = 11 };
+       SW_FIELD_CHAIN_WARPS = 4, SW_FIELD_NB_WARP = 4, SW_FIELD_PREP_WARP = 5, SW_FIELD_WARPS = 10 };
 
 template <class real> struct SweepParams {
     const real *J;
@@ -107,7 +107,8 @@ template <class real> struct SweepParams {
 
 /* shared-memory carve-up, identical on host and device */
 template <class real> struct SweepSmem {
-    size_t field, ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, confAny, accLog, sgnLog, spec, carry, pend, cstate, counter, total;
+    size_t field, ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, confAny, accLog, sgnLog, spec, carry, pend, cstate, flipQ, counter, total;
+    int flipQLen;
     /* fieldElems > 0: field mode -- T rows of fieldElems local fields instead of the TMA ring (stages == 0) */
     __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K, int dotWarps, int fieldElems = 0) {
         size_t o = 0;
@@ -127,8 +128,8 @@ template <class real> struct SweepSmem {
         us = o; o += tab * T * K * sizeof(real);
         hs = o; o += (fieldElems ? 0 : tab) * T * K * sizeof(real); /* field mode keeps h inside its field rows */
         xn = o; o += (size_t)2 * tab * K * 4;
-        conf = o; o += (size_t)2 * 2 * K * 4;
-        confAny = o; o += 32; /* + pubMask[2 buffers][2 sides] */
+        conf = o; o += tab * 2 * K * 4;      /* [tab][2 sides][K] */
+        confAny = o; o += tab * 2 * 4 * 2;   /* [tab][2 sides] + pubMask[tab][2 sides] */
         accLog = o; o += (size_t)2 * T * 4;
         sgnLog = o; o += (size_t)2 * T * 4;
         spec = o; o += (size_t)(2 * T + 2 * T * K) * 4; /* window-parallel chain: trotter info, frontiers, local conflict masks */
@@ -139,6 +140,11 @@ template <class real> struct SweepSmem {
         pend = o; o += (size_t)(fieldElems ? 1 : 0) * T * 32 * sizeof(real);
         cstate = o; o += (size_t)(fieldElems ? 1 : 0) * T * 8 * sizeof(real);
         o = (o + 15) & ~(size_t)15;
+        /* field mode: queue of committed flips (chain warps -> field warps), 64-bit entries (sequence number << 32 | payload).  The
+         * chain cannot be more than two windows ahead of the slowest field warp: 2 (T K flips + 1 marker) entries at most */
+        flipQLen = 0;
+        if (fieldElems) { flipQLen = 64; while (flipQLen < 2 * (T * K + 1) + 2) flipQLen <<= 1; }
+        flipQ = o; o += (size_t)flipQLen * 8;
         counter = o; o += 32;
         total = (o + 127) & ~(size_t)127;
     }
@@ -288,13 +294,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     /* warp roles.  Warps are spread over the SM's four schedulers by (warp & 3): scheduler 0 is kept for the latency-bound
      * accept chain and its helpers, the twelve streaming dot warps share the other three. */
     const bool wide = !FIELD && (P.dotWarps == SW_DOT_WARPS_WIDE);
-    const bool dotWarp = FIELD ? (warp > SW_FIELD_HELPER_WARP) : ((warp & 3) != 0 || (wide && (warp == SW_SNAP_WARP || warp == SW_PREP_WARP)));
-    /* dot warp index: 0..11 for the warps of schedulers 1-3, 12 / 13 for warps 4 / 8 in the wide layout; field mode: warps 5..15 */
-    const int dw = FIELD ? warp - (SW_FIELD_HELPER_WARP + 1) : ((warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : SW_DOT_WARPS + (warp >> 2) - 1);
+    const bool dotWarp = FIELD ? (warp > SW_FIELD_PREP_WARP) : ((warp & 3) != 0 || (wide && (warp == SW_SNAP_WARP || warp == SW_PREP_WARP)));
+    /* dot warp index: 0..11 for the warps of schedulers 1-3, 12 / 13 for warps 4 / 8 in the wide layout; field mode: warps 6..15 */
+    const int dw = FIELD ? warp - (SW_FIELD_PREP_WARP + 1) : ((warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : SW_DOT_WARPS + (warp >> 2) - 1);
     const bool chainWarp = FIELD ? (warp < SW_FIELD_CHAIN_WARPS) : (warp == SW_CHAIN_WARP);
-    const bool snapWarp = !FIELD && !wide && (warp == SW_SNAP_WARP), prepWarp = !FIELD && !wide && (warp == SW_PREP_WARP), nbWarp = !FIELD && !wide && (warp == SW_NB_WARP);
-    /* wide layout: warp 12 builds snapshots, tables and neighbour data in turn; field mode: warp 4 does */
-    const bool allHelperWarp = FIELD ? (warp == SW_FIELD_HELPER_WARP) : (wide && (warp == SW_NB_WARP));
+    const bool snapWarp = !FIELD && !wide && (warp == SW_SNAP_WARP);
+    const bool prepWarp = FIELD ? (warp == SW_FIELD_PREP_WARP) : (!wide && (warp == SW_PREP_WARP));
+    const bool nbWarp = FIELD ? (warp == SW_FIELD_NB_WARP) : (!wide && (warp == SW_NB_WARP));
+    const bool allHelperWarp = !FIELD && wide && (warp == SW_NB_WARP); /* wide layout: warp 12 builds snapshots, tables and neighbour data in turn */
     const int N = P.N, m = P.m;
     const int G = gridDim.x, cta = blockIdx.x;
     const int baseT = m / G, remT = m % G;
@@ -321,10 +328,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     real *carry = reinterpret_cast<real *>(smem + L.carry);  /* FIELD: [maxT][K] */
     real *pend = reinterpret_cast<real *>(smem + L.pend);    /* FIELD: [maxT][32] */
     unsigned char *cstate = smem + L.cstate;                 /* FIELD: [maxT][8 * sizeof(real)] */
+    unsigned long long *flipQ = reinterpret_cast<unsigned long long *>(smem + L.flipQ); /* FIELD: [L.flipQLen] */
     int *xn = reinterpret_cast<int *>(smem + L.xn);          /* [2 sides][3][K] */
-    uint32_t *conf = reinterpret_cast<uint32_t *>(smem + L.conf);       /* [2 buffers][2 sides][K] */
-    uint32_t *confAny = reinterpret_cast<uint32_t *>(smem + L.confAny); /* [2 buffers][2 sides]: rounds with a non-empty mask */
-    uint32_t *pubMask = confAny + 4; /* [2 buffers][2 sides]: rounds of my edge trotter whose accept flag the neighbouring CTA may read */
+    uint32_t *conf = reinterpret_cast<uint32_t *>(smem + L.conf);       /* [TAB][2 sides][K], by window slot */
+    uint32_t *confAny = reinterpret_cast<uint32_t *>(smem + L.confAny); /* [TAB][2 sides]: rounds with a non-empty mask */
+    uint32_t *pubMask = confAny + 2 * TAB; /* [2 buffers][2 sides]: rounds of my edge trotter whose accept flag the neighbouring CTA may read */
     uint32_t *accLog = reinterpret_cast<uint32_t *>(smem + L.accLog);   /* [2 buffers][maxT]: accept bits of a window */
     uint32_t *sgnLog = reinterpret_cast<uint32_t *>(smem + L.sgnLog);   /* [2 buffers][maxT]: spin (1 = up) before each attempt of a window */
     uint32_t *tinfo = reinterpret_cast<uint32_t *>(smem + L.spec);      /* [maxT]: phase | (left local index + 1) << 2 | (right local index + 1) << 8 */
@@ -381,76 +389,82 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     unsigned long long nWaits = 0;
     long long waited = 0; /* cycles lane 0 of this warp spent waiting for another warp or CTA */
 
-    /* helper warp: what chain window wn needs from the neighbouring CTAs -- their snapshot S_{wn-1} and, per attempt of
-     * my edge trotters, the mask of neighbour attempts (previous + current window) that hit the same spin index.
-     * Written to buffer wn & 1 while the chain replays window wn - 1 out of the other buffer. */
+    /* helper warp: what chain window wn needs from the neighbouring CTAs -- their snapshot S_{wn-1} (spins of the two foreign
+     * neighbour trotters before window wn-1), into buffer wn & 1 while the chain replays window wn - 1 out of the other one.
+     * A neighbour hands the flips of a window over as ONE 64-bit word -- tag << 16 | accept bits, written by its chain warp when the
+     * window ends; the spin indices are its Philox draws, which this CTA tabulates itself.  Buffer wn & 1 still holds S_{wn-3}
+     * (built for window wn-2): the flips of windows wn-3 and wn-2 bring it up to date, so nothing is copied. */
+    unsigned long long nbPrevWord = 0ull; /* lanes 0 / 1: the left / right neighbour's word of the window before the newest one */
+    int nbPrevX = 0;                      /* lane (side, j): that window's draw j of the neighbour (its table slot may be gone by now) */
     auto neighbourWindow = [&](int wn) {
-        if (!remote) return;
-        const int Kn = roundsIn(wn), slotN = wn & (TAB - 1), bN = wn & 1;
-        if (wn >= 2) {
-            /* S_{wn-1} of the two foreign neighbours = S_{wn-2} (the buffer window wn-1 uses) with the flips they accepted in
-             * window wn-2.  A neighbour hands those over as ONE 64-bit word per window -- tag << 16 | accept bits, written by
-             * its chain warp when the window ends; the spin indices are its Philox draws, which this CTA tabulates itself. */
-            const unsigned long long *srcB = nbsnap + (size_t)((bN ^ 1) * 2) * NW;
-            unsigned long long *dstB = nbsnap + (size_t)(bN * 2) * NW;
-            for (int i = lane; i < 2 * NW; i += 32) dstB[i] = srcB[i];
-            unsigned long long word = 0ull;
-            if (lane < 2) { /* lane 0 / 1 wait for the left / right neighbour's word of window wn-2 */
-                const int sl = lane ? slotR : slotL;
-                const unsigned long long want = P.snapBase + (unsigned long long)(wn - 1);
-                const unsigned long long *f = sBits + ((size_t)sl * SW_SNAP_SLOTS + ((wn - 2) % SW_SNAP_SLOTS)) * NW;
-                const long long t0 = clock64();
-                unsigned ns = 20;
+        if (!remote || wn < 2) return;
+        const int bN = wn & 1;
+        unsigned long long *dstB = nbsnap + (size_t)(bN * 2) * NW;
+        unsigned long long word = 0ull;
+        if (lane < 2) { /* lane 0 / 1 wait for the left / right neighbour's word of window wn-2 */
+            const int sl = lane ? slotR : slotL;
+            const unsigned long long want = P.snapBase + (unsigned long long)(wn - 1);
+            const unsigned long long *f = sBits + ((size_t)sl * SW_SNAP_SLOTS + ((wn - 2) % SW_SNAP_SLOTS)) * NW;
+            const long long t0 = clock64();
+            unsigned ns = 20;
+            word = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f);
+            while ((word >> 16) != want) {
+                ++nWaits;
+                __nanosleep(ns);
+                if (ns < 160u) ns <<= 1;
                 word = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f);
-                while ((word >> 16) != want) {
-                    ++nWaits;
-                    __nanosleep(ns);
-                    if (ns < 320u) ns <<= 1;
-                    word = ringSharded ? ldRelaxedSys(f) : ldRelaxed(f);
-                }
-                if (lane == 0) waited += clock64() - t0;
             }
-            __syncwarp();
-            const uint32_t mL = (uint32_t)__shfl_sync(0xffffffffu, word, 0) & 0xffffu, mR = (uint32_t)__shfl_sync(0xffffffffu, word, 1) & 0xffffu;
-            const int sideF = lane / K, jF = lane % K;
+            if (lane == 0) waited += clock64() - t0;
+        }
+        __syncwarp();
+        const int sideF = lane / K, jF = lane % K;
+        const int xNew = (sideF < 2) ? xn[(sideF * TAB + ((wn - 2) & (TAB - 1))) * K + jF] : 0;
+#pragma unroll
+        for (int age = 0; age < 2; ++age) { /* age 0: window wn-2 (the new word), age 1: window wn-3 (last call's word and draws) */
+            if (wn - 2 - age < 0) break;
+            const unsigned long long wd = age ? nbPrevWord : word;
+            const uint32_t mL = (uint32_t)__shfl_sync(0xffffffffu, wd, 0) & 0xffffu, mR = (uint32_t)__shfl_sync(0xffffffffu, wd, 1) & 0xffffu;
             if (sideF < 2 && (((sideF ? mR : mL) >> jF) & 1u)) {
-                const int x = xn[(sideF * TAB + ((wn - 2) & (TAB - 1))) * K + jF];
                 int w64, bit;
-                spinBitPos(x, w64, bit);
+                spinBitPos(age ? nbPrevX : xNew, w64, bit);
                 atomicXor(reinterpret_cast<unsigned int *>(dstB + (size_t)sideF * NW + w64) + (bit >> 5), 1u << (bit & 31));
             }
-            __syncwarp();
         }
-        {   /* lane -> (side, round of my edge trotter): which of the neighbour's 2K attempts (previous + this window) drew
-             * the same spin index */
-            const int side = lane / K, rl = lane % K;
-            uint32_t mask = 0;
-            if (side < 2 && rl < Kn) {
-                const int xe = xs[(slotN * maxT + (side ? T - 1 : 0)) * K + rl];
-                const int *xp = xn + (side * TAB + ((wn - 1) & (TAB - 1))) * K;
-                const int *xc = xn + (side * TAB + slotN) * K;
-                if (wn > 0) {
+        nbPrevX = xNew;
+        nbPrevWord = word;
+        __syncwarp();
+    };
+    /* Conflict masks of window v for my two edge trotters (they depend on Philox draws only, so they are built ahead of time, right
+     * after the tables of window v+1): per round r, which of the foreign neighbour's attempts of windows v-1 and v drew the same
+     * spin index (conf), and whether its attempts of windows v / v+1 did -- only then will it ever read my accept flag (pubMask).
+     * Lane (side, r) holds my draw and the neighbour's draw r of the three windows; K lane-addressed shuffles compare all pairs. */
+    auto maskWindow = [&](int v) {
+        if (!remote || v >= nW) return;
+        const int Kv = roundsIn(v), sv = v & (TAB - 1);
+        const int Kq = (v + 1 < nW) ? roundsIn(v + 1) : 0;
+        const int side = lane / K, r = lane % K;
+        const bool act = side < 2;
+        const uint32_t kM = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
+        const int xe = (act && r < Kv) ? xs[(sv * maxT + (side ? T - 1 : 0)) * K + r] : -1 - lane;
+        const int nP = (act && v > 0) ? xn[(side * TAB + ((v - 1) & (TAB - 1))) * K + r] : -100 - lane;
+        const int nC = (act && r < Kv) ? xn[(side * TAB + sv) * K + r] : -100 - lane;
+        const int nQ = (act && r < Kq) ? xn[(side * TAB + ((v + 1) & (TAB - 1))) * K + r] : -100 - lane;
+        uint32_t mP = 0u, mC = 0u, mQ = 0u;
 #pragma unroll
-                    for (int j = 0; j < K; ++j) mask |= (xp[j] == xe ? 1u : 0u) << j;
-                }
-#pragma unroll
-                for (int j = 0; j < K; ++j) mask |= ((j < Kn && xc[j] == xe) ? 1u : 0u) << (K + j);
-                conf[(bN * 2 + side) * K + rl] = mask;
-            }
-            const uint32_t nz = __ballot_sync(0xffffffffu, mask != 0u);
-            if (lane < 2) confAny[bN * 2 + lane] = (nz >> (lane * K)) & ((1u << K) - 1u);
-            /* the other direction: the neighbour reads the accept flag of my round j only when one of ITS attempts of this
-             * window or the next one draws the same spin index, so only those flags are ever published */
-            bool pub = (mask >> K) != 0u;
-            if (side < 2 && rl < Kn && wn + 1 < nW) {
-                const int xe = xs[(slotN * maxT + (side ? T - 1 : 0)) * K + rl];
-                const int *xq = xn + (side * TAB + ((wn + 1) & (TAB - 1))) * K;
-                const int Kq = roundsIn(wn + 1);
-#pragma unroll
-                for (int j = 0; j < K; ++j) pub |= (j < Kq && xq[j] == xe);
-            }
-            const uint32_t pb = __ballot_sync(0xffffffffu, pub);
-            if (lane < 2) pubMask[bN * 2 + lane] = (pb >> (lane * K)) & ((1u << K) - 1u);
+        for (int j = 0; j < K; ++j) {
+            const int src = (lane - r) + j;
+            mP |= (__shfl_sync(0xffffffffu, nP, src) == xe ? 1u : 0u) << j;
+            mC |= (__shfl_sync(0xffffffffu, nC, src) == xe ? 1u : 0u) << j;
+            mQ |= (__shfl_sync(0xffffffffu, nQ, src) == xe ? 1u : 0u) << j;
+        }
+        const bool mine = act && r < Kv;
+        const uint32_t mask = mine ? (mP | (mC << K)) : 0u;
+        if (mine) conf[(sv * 2 + side) * K + r] = mask;
+        const uint32_t nz = __ballot_sync(0xffffffffu, mask != 0u);
+        const uint32_t pb = __ballot_sync(0xffffffffu, mine && (mC | mQ) != 0u);
+        if (lane < 2) {
+            confAny[sv * 2 + lane] = (nz >> (lane * K)) & kM;
+            pubMask[sv * 2 + lane] = (pb >> (lane * K)) & kM;
         }
         __syncwarp();
     };
@@ -515,7 +529,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     __syncthreads();
     if (!FIELD) for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
     for (int i = tid; i < 2 * NW; i += SW_THREADS) nbsnap[2 * NW + i] = nbsnap[i]; /* windows 0 and 1 both start from S_0 */
-    if (warp == (FIELD ? (int)SW_FIELD_HELPER_WARP : (int)SW_NB_WARP)) neighbourWindow(0);
+    if (warp == (FIELD ? (int)SW_FIELD_NB_WARP : (int)SW_NB_WARP)) { /* conflict masks of the windows whose successor's tables exist */
+        constexpr int PW = FIELD ? 4 : 3;
+        for (int v = 0; v < PW - 1; ++v) maskWindow(v);
+        if (nW <= PW) maskWindow(PW - 1);
+    }
     if (FIELD) { /* per-trotter chain state: phase and local neighbours, frontier (rounds of the step that are final), carries */
         if (tid < T) {
             const int gy = gOf(y0 + tid);
@@ -527,6 +545,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             cs[0] = 0u; cs[1] = 0u; cs[2] = 0u; cs[3] = 0u;
         }
         for (int i = tid; i < T * K; i += SW_THREADS) carry[i] = real(0);
+        for (int i = tid; i < L.flipQLen; i += SW_THREADS) flipQ[i] = 0ull;
     }
 
     /* ---------------- hand-off counters between the warps of this CTA (shared memory, release/acquire at CTA scope) ------
@@ -682,43 +701,49 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
      * of 2K-1 per attempt. */
     const int nDot = P.dotWarps;
     const int nGroups = FIELD ? (P.ldF >> 7) : 0;
-    auto applyFlips = [&](int wf) {
-        const int wb = wf & 1, ws = wf & (TAB - 1);
-        for (int t = 0; t < T; ++t) {
-            uint32_t bits = accLog[wb * maxT + t];
-            const uint32_t sg = sgnLog[wb * maxT + t];
-            real *Frow = field + (size_t)t * P.ldF + lane * 4;
-            while (bits) { /* flips in acceptance order: every element sees the same sequence of additions whatever the warp timing */
-                const int rl = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int x = xs[(ws * maxT + t) * K + rl];
-                const real c = ((sg >> rl) & 1u) ? real(-4) : real(4); /* q_old = +1: the sum loses 2 J, h + 2 sum loses 4 J */
-                const real *Jrow = Jr + (size_t)x * P.ldJ + lane * 4;
-                for (int g0 = dw; g0 < nGroups; g0 += nDot * 8) {
-                    typename RowVec4<real>::type v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int g = g0 + u * nDot;
-                        if (g < nGroups) loadRow4(Jrow + (size_t)g * 128, v[u]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int g = g0 + u * nDot;
-                        if (g < nGroups) axpyRow4(Frow + (size_t)g * 128, c, v[u]);
-                    }
-                }
-            }
-        }
-        __syncwarp();
+    /* queue of committed flips: entry = (index + 1) << 32 | payload; payload = marker << 31 | sign << 30 | trotter << 24 | x
+     * (marker entries: window index in the low bits).  Producers take a slot with an atomic add and publish the entry with one
+     * 64-bit store; every field warp reads the queue in order at its own pace. */
+    const uint32_t aFlipQ = smemAddr(flipQ);
+    const uint32_t qMask = (uint32_t)L.flipQLen - 1u;
+    auto pushFlip = [&](uint32_t payload) { /* one lane */
+        const uint32_t slot = atomicAdd(reinterpret_cast<unsigned int *>(taskCounter) + 7, 1u);
+        const unsigned long long e = ((unsigned long long)(slot + 1u) << 32) | payload;
+        asm volatile("st.relaxed.cta.shared.u64 [%0], %1;" ::"r"(aFlipQ + ((slot & qMask) << 3)), "l"(e) : "memory");
     };
-    auto fieldWindow = [&](int w) {
+    /* H[t][.] += c J[x][.] on this warp's column groups (J symmetric), split into the loads and the shared-memory update so
+     * that the loads of the next queued flip are in flight while this one is applied */
+    typedef typename RowVec4<real>::type RowVec;
+    auto loadFlip = [&](int x, RowVec (&v)[8], int g0) {
+        const real *Jrow = Jr + (size_t)x * P.ldJ + lane * 4;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int g = g0 + u * nDot;
+            if (g < nGroups) loadRow4(Jrow + (size_t)g * 128, v[u]);
+        }
+    };
+    auto storeFlip = [&](int t, real c, const RowVec (&v)[8], int g0) {
+        real *Frow = field + (size_t)t * P.ldF + lane * 4;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int g = g0 + u * nDot;
+            if (g < nGroups) axpyRow4(Frow + (size_t)g * 128, c, v[u]);
+        }
+    };
+    auto applyFlip = [&](int t, int x, real c) {
+        for (int g0 = dw; g0 < nGroups; g0 += nDot * 8) {
+            RowVec v[8];
+            loadFlip(x, v, g0);
+            storeFlip(t, c, v, g0);
+        }
+    };
+    auto fieldDots = [&](int w) { /* scaleA H[t][x] for the attempts of window w whose column this warp owns */
         const int Kw = roundsIn(w), buf = w & 1, slot = w & (TAB - 1);
         const int nEnt = T * Kw;
-        if (w >= 2) applyFlips(w - 2);
+        __syncwarp();
         for (int e = lane; e < nEnt; e += 32) {
             const int t = e % T, rl = e / T;
-            const int o = (slot * maxT + t) * K + rl;
-            const int x = xs[o];
+            const int x = xs[(slot * maxT + t) * K + rl];
             if ((x >> 7) % nDot == dw) dots[(buf * maxT + t) * K + rl] = P.scaleA * field[(size_t)t * P.ldF + x];
         }
         /* one count per field warp and window (parity buffers): the chain starts window w at nDot * (w / 2 + 1) */
@@ -729,6 +754,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     if (tid == 0) {
         stReleaseCta(aRowsDone, 0u); stReleaseCta(aRowsDone + 4, 0u); stReleaseCta(aReplayDone, 0u);
         stReleaseCta(aSnapCount, 1u); stReleaseCta(aNbCount, 1u); stReleaseCta(aPrepCount, FIELD ? 4u : 3u);
+        stReleaseCta(aSync + 28, 0u); /* tail of the flip queue (field mode) */
     }
     __syncthreads();
     const long long tLoop0 = clock64();
@@ -738,16 +764,63 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
      * the same time (512 trotters on 148 SMs: 4 or 3 per CTA -> 12 or 9 streaming warps). */
     const int activeDotWarps = max(1, (P.dotWarps * T + maxT - 1) / maxT);
     if (FIELD && dotWarp) {
-        for (int w = 0; w < nW; ++w) {
-            waitCount(aPrepCount, (uint32_t)w + 1u, 20);                 /* tables of window w (and w-1) */
-            if (w >= 2) waitCount(aReplayDone, (uint32_t)w - 1u, 20);    /* window w-2 replayed: its flips are logged, its buffers free */
-            fieldWindow(w);
-        }
-        if (P.writeBackF) { /* the last two windows' flips, so that F matches the final spins; then back to global memory */
-            for (int wf = max(nW - 2, 0); wf < nW; ++wf) {
-                waitCount(aReplayDone, (uint32_t)wf + 1u, 20);
-                applyFlips(wf);
+        /* The field rows hold every flip of the windows <= w when the local fields of window w + 2 are read: the chain warps
+         * queue each flip the moment they commit it (so its row streams in while the chain goes on) and a marker when a window
+         * is complete; a field warp applies the flips in queue order -- per trotter that is commit order, so every element sees
+         * the same sequence of additions whatever the timing -- and on the marker of window w hands over the fields of w + 2. */
+        fieldDots(0);
+        if (nW > 1) fieldDots(1);
+        uint32_t pos = 0;
+        for (;;) {
+            unsigned long long e = 0ull;
+            if (lane == 0) {
+                const uint32_t a = aFlipQ + ((pos & qMask) << 3);
+                unsigned ns = 16u;
+                const long long t0 = clock64();
+                bool slept = false;
+                for (;;) {
+                    asm volatile("ld.relaxed.cta.shared.u64 %0, [%1];" : "=l"(e) : "r"(a) : "memory");
+                    if ((uint32_t)(e >> 32) == pos + 1u) break;
+                    slept = true;
+                    __nanosleep(ns);
+                    if (ns < 128u) ns <<= 1;
+                }
+                if (slept) waited += clock64() - t0;
             }
+            const uint32_t pl = (uint32_t)__shfl_sync(0xffffffffu, e, 0);
+            ++pos;
+            if (pl >> 31) { /* marker: window wm is complete */
+                const int wm = (int)(pl & 0x7fffffffu);
+                if (wm + 2 < nW) {
+                    waitCount(aPrepCount, (uint32_t)wm + 3u, 20); /* tables of window wm + 2 */
+                    fieldDots(wm + 2);
+                }
+                if (wm == nW - 1) break;
+            } else {
+                const int t0 = (int)((pl >> 24) & 63u), x0 = (int)(pl & 0xffffffu);
+                const real c0 = ((pl >> 30) & 1u) ? real(-4) : real(4); /* q_old = +1: h + 2 sum loses 4 J */
+                bool done2 = false;
+                if constexpr (sizeof(real) == 4) if (nGroups <= nDot * 8) { /* one batch of loads per flip: overlap it with the next queued flip, if there is one already (fp32: 64 registers) */
+                    done2 = true;
+                    RowVec va[8], vb[8];
+                    loadFlip(x0, va, dw);
+                    unsigned long long e2 = 0ull;
+                    if (lane == 0) asm volatile("ld.relaxed.cta.shared.u64 %0, [%1];" : "=l"(e2) : "r"(aFlipQ + ((pos & qMask) << 3)) : "memory");
+                    e2 = __shfl_sync(0xffffffffu, e2, 0);
+                    const uint32_t pl2 = (uint32_t)e2;
+                    const bool two = ((uint32_t)(e2 >> 32) == pos + 1u) && !(pl2 >> 31);
+                    if (two) {
+                        ++pos;
+                        loadFlip((int)(pl2 & 0xffffffu), vb, dw);
+                    }
+                    storeFlip(t0, c0, va, dw);
+                    if (two) storeFlip((int)((pl2 >> 24) & 63u), ((pl2 >> 30) & 1u) ? real(-4) : real(4), vb, dw);
+                }
+                if (!done2) applyFlip(t0, x0, c0);
+            }
+        }
+        if (P.writeBackF) { /* H matches the final spins: back to global memory for the next step */
+            __syncwarp();
             for (int t = 0; t < T; ++t)
                 for (int g = dw; g < nGroups; g += nDot) {
                     const size_t o = (size_t)t * P.ldF + (size_t)g * 128 + lane * 4;
@@ -785,12 +858,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         for (int w = 1; w < nW; ++w) {
             waitCount(aReplayDone, (uint32_t)w, 20);
             snapshotWindow(w);
-            if (FIELD) { /* eight table slots: window w+3 goes to the slot of window w-5, which nobody reads any more */
-                if (w + 1 < nW) { neighbourWindow(w + 1); signalCount(aNbCount, (uint32_t)w + 2u); }
-                if (w + 3 < nW) { prepWindow(w + 3, lane, 32); signalCount(aPrepCount, (uint32_t)w + 4u); }
-                continue;
+            if (w + 2 < nW) { /* tables of window w+2, then the conflict masks of window w+1 (they look one window ahead) */
+                prepWindow(w + 2, lane, 32);
+                __syncwarp();
+                maskWindow(w + 1);
+                if (w + 2 == nW - 1) maskWindow(w + 2);
+                signalCount(aPrepCount, (uint32_t)w + 3u);
             }
-            if (w + 2 < nW) { prepWindow(w + 2, lane, 32); signalCount(aPrepCount, (uint32_t)w + 3u); }
             if (w + 1 < nW) { neighbourWindow(w + 1); signalCount(aNbCount, (uint32_t)w + 2u); }
         }
     } else if (nbWarp) {
@@ -805,9 +879,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         /* tables of window wp go to the slot of window wp-4, dead once S_{wp-2} is built (window wp-3 replayed) */
         for (int wp = FIELD ? 4 : 3; wp < nW; ++wp) {
             /* field mode: eight slots, one more window of look-ahead (the dot warps still read window wp-4's slot then) */
-            waitCount(aSnapCount, (uint32_t)wp - (FIELD ? 2u : 1u), 20);
+            if (FIELD) waitCount(aReplayDone, (uint32_t)wp - 3u, 20); /* window wp-4 replayed: the slot of window wp-8 is dead */
+            else waitCount(aSnapCount, (uint32_t)wp - 1u, 20);
             if (!FIELD && remote) waitCount(aNbCount, (uint32_t)wp - 1u, 20); /* the neighbour warp reads window wp-4's draws for window wp-2 */
             prepWindow(wp, lane, 32);
+            __syncwarp();
+            maskWindow(wp - 1); /* the conflict masks look one window ahead */
+            if (wp == nW - 1) maskWindow(wp);
             signalCount(aPrepCount, (uint32_t)wp + 1u);
         }
     } else if (FIELD && chainWarp) {
@@ -843,24 +921,210 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         unsigned long long nAccepted = 0;
         /* profile of chain warp 0 (stats[8..15]): cycles in gather waits / idle polls / the window barrier, evaluation passes,
          * resolves forced by an uncertain attempt / by a second commit, passes that ended on a blocked attempt */
-        long long cycGather = 0, cycIdle = 0, cycBar = 0;
+        long long cycGather = 0, cycIdle = 0, cycBar = 0, cycStart = 0, cycEval = 0, cycEnd = 0, waitedRows = 0, waitedNbF = 0;
         unsigned long long nEval = 0, nUncRes = 0, nCommitRes = 0, nBlkStop = 0;
         auto cst = [&](int t) { return reinterpret_cast<uint32_t *>(cstate + (size_t)t * 8 * sizeof(real)); }; /* [0] pending window + 1, [1] its round, [2] accept bits, [3] sign bits */
         auto cstR = [&](int t) { return reinterpret_cast<real *>(cstate + (size_t)t * 8 * sizeof(real) + 16); }; /* [0] bound, [1] signed scale of the pending generation */
+
+        /* ---- fast path: at most one trotter per chain warp (T <= 4, e.g. 512 trotters on 148 SMs).  Everything a window needs
+         * per attempt is held in registers -- lane r < K: round r of the current window, lane K + r: round r of the next window
+         * (cross-term gathers, local conflict masks of the right-hand neighbour) -- so that an evaluation pass is three
+         * state-dependent shared-memory loads (own spin word, the two neighbours' words), a handful of ALU instructions and a vote. */
+        const bool fast = (T <= CW);
+        const int tF = cw;
+        const bool haveT = fast && (cw < T);
+        const uint32_t infoF = haveT ? tinfo[tF] : 0u;
+        const int phF = (int)(infoF & 3u), tnLF = (int)((infoF >> 2) & 63u) - 1, tnRF = (int)((infoF >> 8) & 63u) - 1;
+        /* does the attempt of the local left / right neighbour in the SAME round come before mine? */
+        const bool precLF = haveT && tnLF >= 0 && (int)(tinfo[tnLF] & 3u) < phF, precRF = haveT && tnRF >= 0 && (int)(tinfo[tnRF] & 3u) < phF;
+        const bool edgeLF = haveT && remote && tnLF < 0, edgeRF = haveT && remote && tnRF < 0;
+        uint32_t pwF = 0u, pr0F = 0u;   /* pending generation of gathers: window it was issued in + 1 (0: none), its round */
+        real pSF = real(0), carryN = real(0); /* its signed scale; lanes K..2K-1: corrections known so far for the next window's rounds */
+        uint32_t needNext = 0u;         /* lane (side, r): rounds of the local neighbour `side` that must be final before round r of the coming window */
+        auto localNeed = [&](int wq) -> uint32_t { /* 16 lane-addressed shuffles instead of K x K shared-memory compares */
+            const int Kq = roundsIn(wq), sq_ = wq & (TAB - 1);
+            const int tn = (hI == 0) ? tnLF : tnRF;
+            const int xm = xs[(sq_ * maxT + tF) * K + rI];
+            const int xnb = (hI < 2 && tn >= 0 && rI < Kq) ? xs[(sq_ * maxT + tn) * K + rI] : -1 - lane;
+            uint32_t msk = 0u;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int got = __shfl_sync(0xffffffffu, xnb, (lane - rI) + j);
+                msk |= (got == xm ? 1u : 0u) << j;
+            }
+            const bool prec = (hI == 0) ? precLF : precRF;
+            msk &= ((1u << rI) - 1u) | ((prec ? 1u : 0u) << rI);
+            return (hI < 2 && tn >= 0 && rI < Kq) ? msk : 0u;
+        };
+        if (SQA && haveT) needNext = localNeed(0);
 
         for (int w = 0; w < nW; ++w) {
             const int Kw = roundsIn(w), KwN = (w + 1 < nW) ? roundsIn(w + 1) : 0;
             const int buf = w & 1, slot = w & (TAB - 1), slotN = (w + 1) & (TAB - 1);
             const uint32_t wBase = (uint32_t)(w * K);
+            const long long wt0 = waited;
             waitCount(aRowsDone + 4u * (uint32_t)buf, (uint32_t)(P.dotWarps * ((w >> 1) + 1)), 0);
+            const long long wt1 = waited;
             if (remote) waitCount(aNbCount, (uint32_t)w + 1u, 0);
+            const long long wt2 = waited;
             waitCount(aPrepCount, (uint32_t)min(w + 2, nW), 0); /* the gathers of a commit look at the next window's draws */
+            waitedRows += wt1 - wt0; waitedNbF += wt2 - wt1;
             const unsigned long long flagBase = (P.roundBase + (unsigned long long)w * K + 1ull) << 1;
             const long long rrBase = (long long)w * K - K; /* round index of bit 0 of a remote conflict mask */
             const int fs0 = (w * K) % SW_FLAG_RING;
             const unsigned long long *nbRowsW = nbsnap + (size_t)buf * 2 * NW;
 
+            if (fast) {
+            const long long tw0 = clock64();
+            if (haveT) {
+                const int t = tF;
+                const int o = (slot * maxT + t) * K + rI;
+                /* per-window constants of my attempt */
+                const uint32_t xbv = (uint32_t)xb[o];
+                const uint32_t aw = (xbv >> 5) << 2, bit = xbv & 31u;
+                const uint32_t aOwn = aMy0 + (uint32_t)t * rowBytes + aw;
+                const uint32_t aL = (tnLF >= 0 ? aMy0 + (uint32_t)tnLF * rowBytes : aNb + (uint32_t)(buf * 2) * rowBytes) + aw;
+                const uint32_t aR = (tnRF >= 0 ? aMy0 + (uint32_t)tnRF * rowBytes : aNb + (uint32_t)(buf * 2 + 1) * rowBytes) + aw;
+                const real lnu = us[o];
+                const int xMine = xs[o];
+                const int xGather = (hI == 0) ? xMine : ((hI == 1 && rI < KwN) ? xs[(slotN * maxT + t) * K + rI] : -1);
+                uint32_t needL = 0u, needR = 0u, cmL = 0u, cmR = 0u;
+                if (SQA) {
+                    needL = needNext; /* lanes 0..K-1 hold the left masks, lanes K..2K-1 the right ones */
+                    needR = __shfl_down_sync(0xffffffffu, needNext, K);
+                    if (hI != 0) { needL = 0u; needR = 0u; }
+                    if (hI == 0 && rI < Kw) { /* neighbours owned by other CTAs: attempts of theirs that precede mine on the same spin index */
+                        const uint32_t precBase = (w > 0 ? kMask : 0u) | (((1u << rI) - 1u) << K);
+                        if (edgeLF) cmL = conf[(slot * 2 + 0) * K + rI] & (precBase | (((nbPhaseL < phF) ? 1u : 0u) << (K + rI)));
+                        if (edgeRF) cmR = conf[(slot * 2 + 1) * K + rI] & (precBase | (((nbPhaseR < phF) ? 1u : 0u) << (K + rI)));
+                    }
+                }
+                const bool rare = (needL | needR | cmL | cmR) != 0u;
+                const uint32_t pmaskW = ((edgeLF && t == 0) ? pubMask[slot * 2] : 0u) | ((edgeRF && t == T - 1) ? pubMask[slot * 2 + 1] : 0u);
+                if (pwF != 0u && pwF != (uint32_t)w) { cpAsyncWaitAll(); pwF = 0u; } /* issued two windows ago: the field rows have the flip by now */
+                real v;
+                ldsReal(aDots + (uint32_t)(((buf * maxT + t) * K + rI) * sizeof(real)), v);
+                v += __shfl_down_sync(0xffffffffu, carryN, K); /* corrections gathered during the previous window */
+                carryN = real(0);
+                uint32_t accC = 0u, sgnC = 0u, fr = 0u;
+                const long long tw1 = clock64();
+                cycStart += tw1 - tw0;
+
+                while (fr < (uint32_t)Kw) {
+                    const bool valid = (hI == 0) && (rI < Kw) && ((uint32_t)rI >= fr);
+                    uint32_t code = 0u; /* 0: final rejection, 1: blocked, 2: uncertain, 3: accept */
+                    uint32_t up = 0u, wv = 0u;
+                    if (valid) {
+                        wv = ldsU32(aOwn);
+                        up = (wv >> bit) & 1u;
+                        real vv = v;
+                        bool blk = false;
+                        if (SQA) {
+                            uint32_t lb = (ldsU32(aL) >> bit) & 1u, rb = (ldsU32(aR) >> bit) & 1u;
+                            if (rare) { /* a neighbour draws this spin index within the look-back range: its earlier attempts must be final */
+                                if (needL) {
+                                    const uint32_t fn = ldAcquireCta(aFront + 4u * (uint32_t)tnLF) - wBase;
+                                    if (needL & ~((fn >= 32u) ? 0xffffffffu : ((1u << fn) - 1u))) blk = true;
+                                    lb = (ldsU32(aL) >> bit) & 1u;
+                                }
+                                if (needR) {
+                                    const uint32_t fn = ldAcquireCta(aFront + 4u * (uint32_t)tnRF) - wBase;
+                                    if (needR & ~((fn >= 32u) ? 0xffffffffu : ((1u << fn) - 1u))) blk = true;
+                                    rb = (ldsU32(aR) >> bit) & 1u;
+                                }
+                                if (cmL) {
+                                    const int q = remoteBitTry(nbRowsW, xMine, cmL, rrBase, P.roundBase, aFlags + (size_t)slotL * SW_FLAG_RING, 0);
+                                    if (q < 0) blk = true; else lb = (uint32_t)q;
+                                }
+                                if (cmR) {
+                                    const int q = remoteBitTry(nbRowsW + NW, xMine, cmR, rrBase, P.roundBase, aFlags + (size_t)slotR * SW_FLAG_RING, 0);
+                                    if (q < 0) blk = true; else rb = (uint32_t)q;
+                                }
+                            }
+                            vv -= nbScale2 * real((int)(lb + rb) - 1);
+                        }
+                        if (blk) code = 1u;
+                        else {
+                            const real sv = up ? vv : -vv;
+                            const bool affected = (pwF != 0u) && (pwF != (uint32_t)w + 1u || (uint32_t)rI > pr0F);
+                            if (affected && fabs(sv - lnu) <= P.uncBound + real(1e-5) * fabs(sv)) code = 2u;
+                            else if (sv < lnu) code = 3u; /* exp(-dE beta) > u */
+                        }
+                    }
+                    const uint32_t stopBits = __ballot_sync(0xffffffffu, code != 0u) & kMask;
+                    ++nEval;
+                    uint32_t newFront = (uint32_t)Kw;
+                    uint32_t kind = 0u;
+                    int rs = Kw;
+                    if (stopBits) {
+                        rs = __ffs(stopBits) - 1;
+                        kind = __shfl_sync(0xffffffffu, code, rs);
+                        newFront = (uint32_t)rs;
+                        if (pwF != 0u && kind >= 2u) { /* the gathers in flight must land before an uncertain attempt is decided / before the next commit */
+                            const long long tg = clock64();
+                            cpAsyncWaitAll();
+                            cycGather += clock64() - tg;
+                            real val;
+                            ldsReal(aPend + (uint32_t)((t * 32 + lane) * sizeof(real)), val);
+                            val *= pSF;
+                            const real fromNext = __shfl_down_sync(0xffffffffu, (hI == 1) ? val : real(0), K);
+                            if (pwF == (uint32_t)w + 1u) { /* issued in this window: lanes < K later rounds of it, lanes K.. the next window */
+                                if (hI == 0) v += val; else if (hI == 1) carryN += val;
+                            } else if (hI == 0) v += fromNext; /* issued in the previous window: its "next window" is this one */
+                            pwF = 0u;
+                        }
+                        if (kind == 3u) { /* commit */
+                            const uint32_t upj = __shfl_sync(0xffffffffu, up, rs);
+                            if (lane == rs) stsU32(aOwn, wv ^ (1u << bit));
+                            const int xF = __shfl_sync(0xffffffffu, xMine, rs);
+                            const real *Jrow = Jr + (size_t)xF * P.ldJ;
+                            const bool want = (hI == 0) ? (rI > rs && rI < Kw) : (xGather >= 0);
+                            const uint32_t aP = aPend + (uint32_t)((t * 32 + lane) * sizeof(real));
+                            if (want) cpAsyncReal(aP, Jrow + xGather); else stsReal(aP, real(0));
+                            cpAsyncCommit();
+                            for (int i = lane; i < rowLines; i += 32) prefetchL2(Jrow + (size_t)i * (128 / sizeof(real)));
+                            pwF = (uint32_t)w + 1u; pr0F = (uint32_t)rs;
+                            pSF = upj ? corrScale : -corrScale;
+                            accC |= 1u << rs; sgnC |= upj << rs;
+                            if (lane == 0) { pushFlip((upj << 30) | ((uint32_t)t << 24) | (uint32_t)xF); ++nAccepted; }
+                            newFront = (uint32_t)rs + 1u;
+                        }
+                    }
+                    if (pmaskW) { /* rounds that became final and whose accept flag a neighbouring CTA may read */
+                        uint32_t pm = pmaskW & ((newFront >= 32u) ? 0xffffffffu : ((1u << newFront) - 1u)) & ~((1u << fr) - 1u);
+                        if (lane == 0) {
+                            unsigned long long *myFlags = aFlags + (size_t)(y0 + t) * SW_FLAG_RING;
+                            while (pm) {
+                                const int r = __ffs(pm) - 1;
+                                pm &= pm - 1;
+                                stRelaxed(myFlags + (fs0 + r) % SW_FLAG_RING, flagBase + (unsigned long long)(2 * r) + ((kind == 3u && r == rs) ? 1ull : 0ull));
+                            }
+                        }
+                    }
+                    if (newFront != fr) {
+                        __syncwarp(); /* the flipped spin word is written before the frontier moves */
+                        if (lane == 0) stReleaseCta(aFront + 4u * (uint32_t)t, wBase + newFront);
+                        fr = newFront;
+                    } else if (kind == 1u) { /* blocked on another warp or CTA */
+                        const long long ti = clock64();
+                        ++nWaits;
+                        __nanosleep(20);
+                        cycIdle += clock64() - ti;
+                    }
+                }
+                const long long tw2 = clock64();
+                cycEval += tw2 - tw1;
+                if (lane == 0 && pmaskW == 0u) {} /* (flags are only published where readable) */
+                if (lane == 0 && remote && (t == 0 || t == T - 1)) /* the neighbouring CTAs rebuild this trotter's spins from the accept bits of the window */
+                    stRelaxed(sBits + ((size_t)(y0 + t) * SW_SNAP_SLOTS + (size_t)(w % SW_SNAP_SLOTS)) * NW,
+                              ((P.snapBase + (unsigned long long)w + 1ull) << 16) | (unsigned long long)accC);
+                (void)sgnC;
+                if (SQA && w + 1 < nW) needNext = localNeed(w + 1); /* while the slower trotters of the CTA finish the window */
+                cycEnd += clock64() - tw2;
+            }
+            } else {
             /* window start: the corrections carried over from the previous window, the local conflict masks, the logs */
+            const long long tw0 = clock64();
             for (int t = cw; t < T; t += CW) {
                 uint32_t *cs = cst(t);
                 if (cs[0] != 0u && cs[0] != (uint32_t)w) { /* a generation issued two windows ago: F has the flip by now */
@@ -872,25 +1136,25 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                     const int o = (buf * maxT + t) * K + rI;
                     dots[o] += carry[t * K + rI];
                     carry[t * K + rI] = real(0);
-                    if (SQA) {
-                        const uint32_t info = tinfo[t];
-                        const int x = xs[(slot * maxT + t) * K + rI];
+                }
+                if (SQA) { /* rounds of a local neighbour that draw the same spin index: my draws in lanes 0..K-1, the neighbour's in lanes K..2K-1, one MATCH */
+                    const uint32_t info = tinfo[t];
+                    const int xMine = (hI == 0 && rI < Kw) ? xs[(slot * maxT + t) * K + rI] : -1 - lane;
 #pragma unroll
-                        for (int side = 0; side < 2; ++side) {
-                            const int tn = (int)((info >> (2 + 6 * side)) & 63u) - 1;
-                            uint32_t msk = 0;
-                            if (tn >= 0) {
-                                const int *xo = xs + (slot * maxT + tn) * K;
-#pragma unroll
-                                for (int j = 0; j < K; ++j) msk |= ((j < Kw && xo[j] == x) ? 1u : 0u) << j;
-                            }
-                            lconf[(t * 2 + side) * K + rI] = msk;
-                        }
+                    for (int side = 0; side < 2; ++side) {
+                        const int tn = (int)((info >> (2 + 6 * side)) & 63u) - 1;
+                        if (tn >= 0) { /* warp-uniform */
+                            const int v = (hI == 1 && rI < Kw) ? xs[(slot * maxT + tn) * K + rI] : xMine;
+                            const uint32_t mm = __match_any_sync(0xffffffffu, v);
+                            if (hI == 0) lconf[(t * 2 + side) * K + rI] = (rI < Kw) ? ((mm >> K) & kMask) : 0u;
+                        } else if (hI == 0) lconf[(t * 2 + side) * K + rI] = 0u;
                     }
                 }
                 if (lane == 0) { cs[2] = 0u; cs[3] = 0u; }
             }
             __syncwarp();
+            const long long tw1 = clock64();
+            cycStart += tw1 - tw0;
 
             for (;;) {
                 bool allDone = true, progress = false;
@@ -933,7 +1197,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                                     nbit = (ldsU32(aMy0 + (uint32_t)tn * rowBytes + aw) >> bit) & 1u;
                                 } else {
                                     nbit = (ldsU32(aNb + (uint32_t)(buf * 2 + side) * rowBytes + aw) >> bit) & 1u;
-                                    const uint32_t cm = conf[(buf * 2 + side) * K + rI];
+                                    const uint32_t cm = conf[(slot * 2 + side) * K + rI];
                                     if (cm) { /* rare: so does the neighbour owned by another CTA -- its accept flags decide */
                                         const uint32_t prec = (w > 0 ? kMask : 0u) | (((1u << rI) - 1u) << K) |
                                                               ((((side ? nbPhaseR : nbPhaseL) < ph) ? 1u : 0u) << (K + rI));
@@ -1000,13 +1264,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                             cs[0] = (uint32_t)w + 1u; cs[1] = (uint32_t)rs;
                             cs[2] |= 1u << rs; cs[3] |= upj << rs;
                             cstR(t)[0] = P.uncBound;
+                            pushFlip((upj << 30) | ((uint32_t)t << 24) | (uint32_t)xs[oS]);
                             cstR(t)[1] = upj ? corrScale : -corrScale;
                             ++nAccepted;
                         }
                         newFront = (uint32_t)rs + 1u;
                     }
                     if (lane == 0 && remote && (t == 0 || t == T - 1)) { /* rounds that became final and whose accept flag a neighbouring CTA may read */
-                        uint32_t pmask = ((t == 0 && !((info >> 2) & 63u)) ? pubMask[buf * 2] : 0u) | ((t == T - 1 && !((info >> 8) & 63u)) ? pubMask[buf * 2 + 1] : 0u);
+                        uint32_t pmask = ((t == 0 && !((info >> 2) & 63u)) ? pubMask[slot * 2] : 0u) | ((t == T - 1 && !((info >> 8) & 63u)) ? pubMask[slot * 2 + 1] : 0u);
                         pmask &= ((newFront >= 32u) ? 0xffffffffu : ((1u << newFront) - 1u)) & ~((1u << fr) - 1u);
                         unsigned long long *myFlags = aFlags + (size_t)(y0 + t) * SW_FLAG_RING;
                         while (pmask) {
@@ -1031,34 +1296,49 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 }
             }
 
+            const long long tw2 = clock64();
+            cycEval += tw2 - tw1;
             for (int t = cw; t < T; t += CW) {
                 if (lane == 0) {
                     const uint32_t accC = cst(t)[2];
-                    accLog[buf * maxT + t] = accC;
-                    sgnLog[buf * maxT + t] = cst(t)[3];
                     if (remote && (t == 0 || t == T - 1)) /* the neighbouring CTAs rebuild this trotter's spins from the accept bits of the window */
                         stRelaxed(sBits + ((size_t)(y0 + t) * SW_SNAP_SLOTS + (size_t)(w % SW_SNAP_SLOTS)) * NW,
                                   ((P.snapBase + (unsigned long long)w + 1ull) << 16) | (unsigned long long)accC);
                 }
             }
+            }
             __syncwarp();
             const long long tb = clock64();
             namedBarSync(1, 32 * CW); /* every trotter of the CTA has finished the window */
             cycBar += clock64() - tb;
-            if (cw == 0) signalCount(aReplayDone, (uint32_t)w + 1u);
+            if (cw == 0) {
+                if (lane == 0) pushFlip(0x80000000u | (uint32_t)w); /* after every flip of the window */
+                signalCount(aReplayDone, (uint32_t)w + 1u);
+            }
         }
         cpAsyncWaitAll();
         if (P.stats) {
             if (lane == 0 && nAccepted) atomicAdd(P.stats, nAccepted);
             if (lane == 0 && cw == 0) {
-                atomicAdd(P.stats + 4, (unsigned long long)waited);
+                atomicAdd(P.stats + 4, (unsigned long long)waitedRows);                      /* waiting for the field warps */
+                atomicAdd(P.stats + 7, (unsigned long long)waitedNbF);                       /* waiting for neighbour data (other CTAs) */
+                atomicAdd(P.stats + 6, (unsigned long long)(waited - waitedRows - waitedNbF)); /* waiting for the Philox tables */
                 atomicAdd(P.stats + 8, (unsigned long long)cycGather);
                 atomicAdd(P.stats + 9, (unsigned long long)cycIdle);
                 atomicAdd(P.stats + 10, (unsigned long long)cycBar);
                 atomicAdd(P.stats + 11, nEval);
-                atomicAdd(P.stats + 12, nUncRes);
-                atomicAdd(P.stats + 13, nCommitRes);
-                atomicAdd(P.stats + 14, nBlkStop);
+                atomicAdd(P.stats + 12, (unsigned long long)cycStart);
+                atomicAdd(P.stats + 13, (unsigned long long)cycEval);
+                atomicAdd(P.stats + 14, (unsigned long long)cycEnd);
+            }
+            if (lane == 0 && cw != 0) atomicAdd(P.stats + 15, (unsigned long long)cycBar); /* chain warps 1..3: cycles waiting in the window barrier */
+            if (lane == 0 && cw == 0 && blockIdx.y == 0) { /* per-CTA profile of the last launch (chain warp 0) */
+                unsigned long long *pc = P.stats + 16 + 8 * (size_t)cta;
+                unsigned long long gt;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+                pc[0] = (unsigned long long)T; pc[1] = (unsigned long long)waitedRows; pc[2] = (unsigned long long)waitedNbF;
+                pc[3] = (unsigned long long)(cycStart + cycEval + cycEnd); pc[4] = (unsigned long long)((clock64() - tLoop0));
+                pc[5] = gt; pc[6] = nAccepted; pc[7] = nEval;
             }
         }
         } /* if constexpr (FIELD) */
@@ -1140,16 +1420,16 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             const uint32_t aLeft = lLocal ? aLeftLocal : aNb + (uint32_t)(buf * 2) * rowBytes;
             const uint32_t aRight = rLocal ? aRightLocal : aNb + (uint32_t)(buf * 2 + 1) * rowBytes;
             uint32_t cmask = 0; /* rounds in which a neighbour owned by another CTA attempts the same spin index */
-            if (remoteLane) cmask = (lLocal ? 0u : confAny[buf * 2]) | (rLocal ? 0u : confAny[buf * 2 + 1]);
+            if (remoteLane) cmask = (lLocal ? 0u : confAny[slot * 2]) | (rLocal ? 0u : confAny[slot * 2 + 1]);
             uint32_t pmask = 0; /* rounds whose accept flag a neighbouring CTA may read */
-            if (publishes) pmask = ((lane == 0 && !lLocal) ? pubMask[buf * 2] : 0u) | ((lane == T - 1 && !rLocal) ? pubMask[buf * 2 + 1] : 0u);
+            if (publishes) pmask = ((lane == 0 && !lLocal) ? pubMask[slot * 2] : 0u) | ((lane == T - 1 && !rLocal) ? pubMask[slot * 2 + 1] : 0u);
             uint32_t pXb = aXb + (uint32_t)(((slot * maxT + tl) * K) * 4);
             uint32_t pUs = aUs + (uint32_t)(((slot * maxT + tl) * K) * sizeof(real));
             uint32_t pDot = aDots + (uint32_t)(((buf * maxT + tl) * K) * sizeof(real));
             const uint32_t aDotsW = aDots + (uint32_t)((buf * maxT * K) * sizeof(real));                             /* dots of this window, [t][round] */
             const uint32_t aCrossW = aCross + (uint32_t)(((FIELD ? (w & 3) : buf) * maxT * K * 2 * K + K) * sizeof(real)); /* this window's columns of [t][round][2K] */
             const uint32_t aXsW = aXs + (uint32_t)(((slot * maxT + tl) * K) * 4);
-            const uint32_t aConfW = aConf + (uint32_t)((buf * 2 * K) * 4);
+            const uint32_t aConfW = aConf + (uint32_t)((slot * 2 * K) * 4);
             const unsigned long long flagBase = (P.roundBase + (unsigned long long)w * K + 1ull) << 1;
             const long long rrBase = (long long)w * K - K; /* round index of bit 0 of a conflict mask */
             int fs = (w * K) % SW_FLAG_RING;
@@ -1220,7 +1500,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                                         }
                                     } else {
                                         nbit = (ldsU32(aNb + (uint32_t)(buf * 2 + side) * rowBytes + aw) >> bit) & 1u;
-                                        const uint32_t cm = conf[(buf * 2 + side) * K + rI];
+                                        const uint32_t cm = conf[(slot * 2 + side) * K + rI];
                                         if (cm) { /* rare: so does the neighbour owned by another CTA -- its accept flags decide */
                                             const uint32_t prec = (w > 0 ? ((1u << K) - 1u) : 0u) | (((1u << rI) - 1u) << K) |
                                                                   ((((side ? nbPhaseR : nbPhaseL) < ph) ? 1u : 0u) << (K + rI));
@@ -1411,7 +1691,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             if (dotWarp && dw == 0) atomicAdd(P.stats + 2, (unsigned long long)busy); /* dot warp 0: cycles spent on dot products */
             if (chainWarp && warp == 0) atomicAdd(P.stats + 3, (unsigned long long)busy); /* chain warp (field mode: the first of four): cycles spent replaying */
             if (snapWarp || nbWarp || allHelperWarp) atomicAdd(P.stats + 5, (unsigned long long)busy); /* snapshot + neighbour (or all-helper) warps */
-            if (prepWarp) atomicAdd(P.stats + 6, (unsigned long long)busy);           /* prep warp: Philox tables */
+            if (prepWarp && !FIELD) atomicAdd(P.stats + 6, (unsigned long long)busy);  /* prep warp: Philox tables (field mode: chain cycles waiting for them) */
         }
     }
 }
@@ -1445,6 +1725,18 @@ __global__ void ringSpinDotKernel(const signed char *q, int ldq, int N, int m, l
     for (int x = threadIdx.x; x < N; x += blockDim.x) s += (int)a[x] * (int)b[x];
     s = warpSum(s);
     if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)out, (unsigned long long)(long long)s);
+}
+
+/* synthetic problems generated on the device (benchmarks, multi-GPU tests): W symmetric, W[i][j] = W[j][i] ~ U(-0.5, 0.5) from
+ * Philox(seed, 0, DOM_PROBLEM, min(i,j), max(i,j)); optionally rounded to the 2^-14 grid the reference tests use
+ * (sqaodpy/tests/example_problems.py:16-22), which keeps every sum exact */
+template <class real> __global__ void randomSymmetricKernel(real *W, int ldW, int N, unsigned long long seed, int quantize) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= N) return;
+    const Philox4 p = sqbPhilox(seed, 0ull, DOM_PROBLEM, (uint32_t)min(i, j), (uint32_t)max(i, j));
+    double u = (double)p.w[0] * (1.0 / 4294967296.0) - 0.5;
+    if (quantize) u = rint(u * 16384.0) * (1.0 / 16384.0);
+    W[(size_t)i * ldW + j] = (real)u;
 }
 
 /* out[i] = max_j |A[i][j]| -- one warp per row (field mode: bound of a cross term whose gather is still in flight) */
@@ -1581,17 +1873,52 @@ template <class real> void B200DenseGraphAnnealer<real>::setQUBO(const HostMatri
     om_ = om;
     /* QUBO -> Ising on the device (formulas.cu); maximize negates W first (CUDADenseGraphAnnealer.cu:148-149) */
     ldJ_ = sq::roundUp(N_, 128);
+    DevBuf<real> dW;
+    dW.alloc(dev_, (size_t)N_ * ldJ_);
+    dev_->h2d2D(dW.p, sizeof(real) * ldJ_, W.data, sizeof(real) * W.stride, sizeof(real) * N_, N_);
+    hamiltonianFromDeviceQUBO(dW.p);
+}
+
+template <class real> void B200DenseGraphAnnealer<real>::hamiltonianFromDeviceQUBO(const real *dW) {
     dJ_.alloc(dev_, (size_t)N_ * ldJ_);
     dh_.alloc(dev_, N_);
-    DevBuf<real> dW, dc;
-    dW.alloc(dev_, (size_t)N_ * ldJ_);
+    DevBuf<real> dc;
     dc.alloc(dev_, 1);
-    dev_->h2d2D(dW.p, sizeof(real) * ldJ_, W.data, sizeof(real) * W.stride, sizeof(real) * N_, N_);
-    devDenseHamiltonian<real>(*dev_, dh_.p, dJ_.p, ldJ_, dc.p, dW.p, ldJ_, N_, om == sq::optMaximize ? real(-1) : real(1));
+    devDenseHamiltonian<real>(*dev_, dh_.p, dJ_.p, ldJ_, dc.p, dW, ldJ_, N_, om_ == sq::optMaximize ? real(-1) : real(1));
     prepareTensorCoreOperand();
     dev_->d2h(&c_, dc.p, sizeof(real));
     dev_->synchronize();
     setState(solProblemSet);
+}
+
+/* extras (no reference counterpart): a synthetic random QUBO generated on the device, see randomSymmetricKernel */
+template <class real> void B200DenseGraphAnnealer<real>::setQUBORandom(int N, unsigned long long seed, bool quantize, sq::OptimizeMethod om) {
+    sqb_throwErrorIf(N < 1, "%s: N must be positive.", __func__);
+    sqb_throwErrorIf(dev_ == NULL, "Device not set.");
+    clearState(solProblemSet);
+    fieldsValid_ = false;
+    if (nProblems_ > 1) { nProblems_ = 1; nReplicas_ = 1; cBatch_.clear(); }
+    N_ = N;
+    m_ = N_ / 4;
+    om_ = om;
+    ldJ_ = sq::roundUp(N_, 128);
+    DevBuf<real> dW;
+    dW.alloc(dev_, (size_t)N_ * ldJ_);
+    randomSymmetricKernel<real><<<dim3((N_ + 255) / 256, N_), 256, 0, dev_->stream()>>>(dW.p, ldJ_, N_, seed, quantize ? 1 : 0);
+    CUDA_CHECK(cudaGetLastError());
+    ++dev_->launchCount;
+    hamiltonianFromDeviceQUBO(dW.p);
+}
+template <class real> void B200DenseGraphAnnealer<real>::getQUBORandom(real *W, int N, int ldW, unsigned long long seed, bool quantize) const {
+    sqb_throwErrorIf(dev_ == NULL, "Device not set.");
+    const int ld = sq::roundUp(N, 128);
+    DevBuf<real> dW;
+    dW.alloc(dev_, (size_t)N * ld);
+    randomSymmetricKernel<real><<<dim3((N + 255) / 256, N), 256, 0, dev_->stream()>>>(dW.p, ld, N, seed, quantize ? 1 : 0);
+    CUDA_CHECK(cudaGetLastError());
+    ++dev_->launchCount;
+    dev_->d2h2D(W, sizeof(real) * ldW, dW.p, sizeof(real) * ld, sizeof(real) * N, N);
+    dev_->synchronize();
 }
 
 template <class real>
@@ -1773,7 +2100,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
         if (fieldRefreshWanted_ > 0) fieldRefresh_ = fieldRefreshWanted_;
     }
     allocHandoff();
-    dStats_.alloc(dev_, 16);
+    dStats_.alloc(dev_, 16 + 8 * (size_t)dev_->numSMs());
     launchCount_ = 0;
     CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(true, K_, fieldMode_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
     CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(false, K_, fieldMode_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
@@ -2130,6 +2457,14 @@ template <class real> void B200DenseGraphAnnealer<real>::getCounters(unsigned lo
         dev_->d2h(out, dStats_.p, 8 * sizeof(unsigned long long));
         dev_->synchronize();
     }
+}
+template <class real> int B200DenseGraphAnnealer<real>::getCtaProfile(unsigned long long *out, int maxCtas) const {
+    const int n = std::min(maxCtas, std::min(grid_, dev_->numSMs()));
+    if (dStats_.p && n > 0) {
+        dev_->d2h(out, dStats_.p + 16, (size_t)n * 8 * sizeof(unsigned long long));
+        dev_->synchronize();
+    }
+    return n;
 }
 template <class real> void B200DenseGraphAnnealer<real>::getProfile(unsigned long long out[16]) const {
     for (int i = 0; i < 16; ++i) out[i] = 0;

@@ -20,6 +20,20 @@ void throwErrorAt(const char *file, unsigned long line, const char *fmt, ...) {
     throw std::runtime_error(buf);
 }
 
+void throwErrorAt(const char *file, unsigned long line) { throwErrorAt(file, line, "Error"); }
+
+/* internal invariant violated: print and abort (reference: common/defines.cpp:12-26) */
+void abortAt(const char *file, unsigned long line, const char *fmt, ...) {
+    char msg[512];
+    va_list va;
+    va_start(va, fmt);
+    vsnprintf(msg, sizeof(msg), fmt, va);
+    va_end(va);
+    fprintf(stderr, "%s:%d %s\n", file, (int)line, msg);
+    abort();
+}
+void abortAt(const char *file, unsigned long line) { abortAt(file, line, "aborted"); }
+
 void log(const char *fmt, ...) {
     static int verbose = -1;
     if (verbose < 0) {

@@ -9,7 +9,7 @@
 
 namespace sqb {
 
-enum { DOM_DENSE_SWEEP = 0, DOM_RANDOMIZE = 1, DOM_BG_SIDE0 = 2, DOM_BG_SIDE1 = 3, DOM_RANDOMIZE1 = 4 };
+enum { DOM_DENSE_SWEEP = 0, DOM_RANDOMIZE = 1, DOM_BG_SIDE0 = 2, DOM_BG_SIDE1 = 3, DOM_RANDOMIZE1 = 4, DOM_PROBLEM = 5 };
 
 struct Philox4 { uint32_t w[4]; };
 

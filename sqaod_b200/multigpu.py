@@ -159,9 +159,16 @@ class RingShardedDenseAnnealer(object):
         assert dist.is_available() and dist.is_initialized(), 'RingShardedDenseAnnealer needs torch.distributed'
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.m = int(n_trotters if n_trotters is not None else W.shape[0] // 4)
         opt = solvers.minimize if int(optimize) == 0 else solvers.maximize
-        self.ann = solvers.dense_graph_annealer(W, opt, dtype)
+        if isinstance(W, tuple) and W[0] == 'random':
+            # ('random', N, seed[, quantize]): the same synthetic W generated on every GPU (no host matrix, no upload: 4 GiB at N = 32768)
+            n = int(W[1])
+            self.ann = solvers.dense_graph_annealer(None, opt, dtype)
+            self.ann.set_qubo_random(n, int(W[2]), bool(W[3]) if len(W) > 3 else False, opt)
+        else:
+            n = W.shape[0]
+            self.ann = solvers.dense_graph_annealer(W, opt, dtype)
+        self.m = int(n_trotters if n_trotters is not None else n // 4)
         self.ann.ring_configure(self.rank, self.world, self.m)
         self.m_local = self.m // self.world
         self._attached = False

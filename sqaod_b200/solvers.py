@@ -99,6 +99,17 @@ class DenseGraphAnnealer(_SolverBase):
         _lib.check(L.sqb_dg_annealer_set_qubo(self._cobj, ptr(W), W.shape[0], W.strides[0] // W.itemsize, int(optimize), self._dt))
         self._optimize = optimize
 
+    def set_qubo_random(self, N, seed, quantize=False, optimize=minimize):
+        """synthetic symmetric W ~ U(-0.5, 0.5), generated on the device (no host matrix, no upload); see get_qubo_random."""
+        _lib.check(L.sqb_dg_annealer_set_qubo_random(self._cobj, int(N), C.c_ulonglong(int(seed)), int(bool(quantize)), int(optimize), self._dt))
+        self._optimize = optimize
+
+    def get_qubo_random(self, N, seed, quantize=False):
+        """the matrix set_qubo_random(N, seed, quantize) anneals, as a host array"""
+        W = np.empty((N, N), self.dtype)
+        _lib.check(L.sqb_dg_annealer_get_qubo_random(self._cobj, ptr(W), int(N), int(N), C.c_ulonglong(int(seed)), int(bool(quantize)), self._dt))
+        return W
+
     def set_qubo_batch(self, Ws, optimize=minimize):
         """a batch of DIFFERENT problems of one size, annealed side by side in one launch per step (problem r uses seed + r).
         Ws: array (n_problems, N, N) of symmetric matrices.  get_E / get_spins / get_q then return n_problems * n_trotters rows,
@@ -220,6 +231,12 @@ class DenseGraphAnnealer(_SolverBase):
         _lib.check(L.sqb_dg_annealer_get_sweep_mode(self._cobj, C.byref(v), self._dt))
         return 'field' if v.value else 'classic'
 
+    def get_cta_profile(self):
+        """per-CTA profile of the last field-mode sweep: array (n_ctas, 8), see sqb_dg_annealer_get_cta_profile"""
+        out = np.zeros((512, 8), np.uint64); n = C.c_int(0)
+        _lib.check(L.sqb_dg_annealer_get_cta_profile(self._cobj, ptr(out), 512, C.byref(n), self._dt))
+        return out[:n.value]
+
     def get_stats(self):
         a = C.c_ulonglong(0); w = C.c_ulonglong(0)
         _lib.check(L.sqb_dg_annealer_get_stats(self._cobj, C.byref(a), C.byref(w), self._dt))
@@ -234,7 +251,7 @@ class DenseGraphAnnealer(_SolverBase):
                 'chain_wait_rows_cycles': raw[4], 'chain_wait_neighbour_cycles': raw[7],
                 'chain_gather_wait_cycles': prof[8], 'chain_idle_cycles': prof[9], 'chain_barrier_cycles': prof[10],
                 'chain_eval_passes': prof[11], 'chain_uncertain_resolves': prof[12], 'chain_commit_resolves': prof[13],
-                'chain_blocked_stops': prof[14]}
+                'chain_blocked_stops': prof[14], 'chain_barrier_cycles_others': prof[15]}
 
 
 def dense_graph_annealer(W=None, optimize=minimize, dtype=np.float64, device=None, **prefs):

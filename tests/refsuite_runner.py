@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Run the REFERENCE's own Python test-suite (sqaodpy/tests, staged unmodified under oracle/_ref/refsuite by
+`make -C oracle glue`) with `sqaod.cuda` bound to libsqaod_b200.so.
+
+    python tests/refsuite_runner.py glue [pytest args]   the reference's CPython glue (sqaodc/pyglue/*.inc +
+                                                         sqaodpy/sqaod/cuda/src/cuda_*.cpp), compiled unmodified against
+                                                         include/sqaodc/sqaodc.h and linked to libsqaod_b200.so
+    python tests/refsuite_runner.py cext [pytest args]   sqaod_b200.cext (the ctypes restatement of the same method tables)
+
+The reference's top-level sqaod/__init__.py imports the CPU extension (needs Eigen: not buildable here), so the package
+object is assembled here instead: sqaod.common, sqaod.py and sqaod.cuda (device.py, the four solver wrappers, formulas.py)
+are the reference's files; only the six C-extension modules underneath sqaod.cuda are ours.  sqaod.cpu is a stub, and the
+CPU test classes are deselected (-k cuda)."""
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SUITE = os.path.join(ROOT, 'oracle', '_ref', 'refsuite')
+CEXT = ['cuda_device', 'cuda_dg_annealer', 'cuda_bg_annealer', 'cuda_dg_bf_searcher', 'cuda_bg_bf_searcher', 'cuda_formulas']
+
+
+def assemble(binding):
+    sys.path.insert(0, SUITE)
+    if binding == 'cext':
+        sys.path.insert(1, ROOT)
+    pkg = types.ModuleType('sqaod')
+    pkg.__path__ = [os.path.join(SUITE, 'sqaod')]
+    sys.modules['sqaod'] = pkg
+    c = importlib.import_module('sqaod.common')
+    pref = importlib.import_module('sqaod.common.preference')
+    pkg.algorithm, pkg.minimize, pkg.maximize = pref.algorithm, pref.minimize, pref.maximize
+    for k in dir(c):
+        if not k.startswith('_'):
+            setattr(pkg, k, getattr(c, k))
+    pkg.common = c
+    pkg.is_cuda_available = lambda: True
+    pkg.py = importlib.import_module('sqaod.py')
+    for name in CEXT:
+        full = 'sqaod.cuda.' + name
+        if binding == 'glue':
+            spec = importlib.util.spec_from_file_location(full, os.path.join(SUITE, 'glue', name + '.so'))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+        else:
+            mod = importlib.import_module('sqaod_b200.cext.' + name)
+        sys.modules[full] = mod
+    pkg.cuda = importlib.import_module('sqaod.cuda')
+
+    class _NoCPU(types.ModuleType):
+        def __getattr__(self, name):
+            raise AttributeError('sqaod.cpu is not part of this run (%s)' % name)
+    pkg.cpu = _NoCPU('sqaod.cpu')
+    return pkg
+
+
+def main():
+    binding = sys.argv[1] if len(sys.argv) > 1 else 'glue'
+    if not os.path.isdir(os.path.join(SUITE, 'tests')):
+        print('REFSUITE_ABSENT')
+        return 0
+    assemble(binding)
+    import pytest
+    args = [os.path.join(SUITE, 'tests'), '-q', '-p', 'no:cacheprovider', '-k', 'cuda and not version', '--rootdir', SUITE,
+            '-o', 'python_files=test_*.py', '-rfE', '--tb=short'] + sys.argv[2:]
+    rc = pytest.main(args)
+    print('REFSUITE_RC %s %d' % (binding, int(rc)))
+    return int(rc)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

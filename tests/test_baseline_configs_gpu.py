@@ -22,12 +22,23 @@ def sq():
     return sqaod_b200
 
 
-def _dense_one_step_vs_oracle(sq, oracle, W, m, mode, seeds, G, beta, steps=1):
+def _device_problem(sq, N, seed):
+    """quantised symmetric W generated on the device (seconds instead of minutes at N = 32768); the host copy feeds the oracle"""
+    gen = sq.dense_graph_annealer(None, sq.minimize, np.float32)
+    return gen.get_qubo_random(N, seed, True)
+
+
+def _dense_one_step_vs_oracle(sq, oracle, W, m, mode, seeds, G, beta, steps=1, random_spec=None):
     workers = oracle.num_threads()
     for seed in seeds:
         ref = oracle.DenseGraphAnnealer(W, 0, np.float32, n_trotters=m, algorithm='coloring', n_workers=workers, rng='philox')
         ref.seed(seed); ref.prepare(); ref.randomize_spin()
-        ann = sq.dense_graph_annealer(W, sq.minimize, np.float32, n_trotters=m)
+        if random_spec is None:
+            ann = sq.dense_graph_annealer(W, sq.minimize, np.float32, n_trotters=m)
+        else:   # the same matrix, generated in place on the device
+            ann = sq.dense_graph_annealer(None, sq.minimize, np.float32)
+            ann.set_qubo_random(random_spec[0], random_spec[1], True)
+            ann.set_preferences(n_trotters=m)      # after the problem: setting a problem resets m to N / 4, as in the reference
         ann.set_sweep_mode(mode, 0)
         ann.seed(seed); ann.prepare(); ann.randomize_spin()
         assert ann.get_sweep_mode() == mode
@@ -49,24 +60,31 @@ def _dense_one_step_vs_oracle(sq, oracle, W, m, mode, seeds, G, beta, steps=1):
     pytest.fail('every seed hit a borderline accept test')
 
 
-@pytest.mark.parametrize('mode', ['classic', 'field'])
-def test_c2_one_step_equals_oracle(sq, oracle, mode):
-    W = quantized_symmetric_W(8192, 8192, np.float32)
-    _dense_one_step_vs_oracle(sq, oracle, W, 512, mode, (3, 4, 5, 6), 0.01, 50.0)
+@pytest.fixture(scope='module')
+def w_c2(sq):
+    return _device_problem(sq, 8192, 8192)
+
+
+@pytest.fixture(scope='module')
+def w_c5b(sq):
+    return _device_problem(sq, 32768, 32768)
+
+
+def test_device_generated_problem_is_what_it_says(sq, w_c2):
+    assert np.array_equal(w_c2, w_c2.T) and np.abs(w_c2).max() <= 0.5
+    assert np.array_equal(np.rint(w_c2 * 16384), w_c2 * 16384)                   # on the 2^-14 grid
+    assert abs(float(w_c2.mean())) < 1e-3 and abs(float(w_c2.std()) - 12 ** -0.5) < 1e-3
 
 
 @pytest.mark.parametrize('mode', ['classic', 'field'])
-def test_c5b_row_length_32768_equals_oracle(sq, oracle, mode):
+def test_c2_one_step_equals_oracle(sq, oracle, w_c2, mode):
+    _dense_one_step_vs_oracle(sq, oracle, w_c2, 512, mode, (3, 4, 5, 6), 0.01, 50.0, random_spec=(8192, 8192))
+
+
+@pytest.mark.parametrize('mode', ['classic', 'field'])
+def test_c5b_row_length_32768_equals_oracle(sq, oracle, w_c5b, mode):
     """N = 32768: J is 4 GiB, byte offsets of rows exceed 2^32.  Four trotters (one per CTA), one step."""
-    N = 32768
-    rng = np.random.default_rng(32768)
-    W = rng.random((N, N), dtype=np.float32)
-    W -= np.float32(0.5)
-    W = np.triu(W)
-    W += np.triu(W, 1).T
-    np.rint(W * np.float32(16384), out=W)
-    W /= np.float32(16384)
-    _dense_one_step_vs_oracle(sq, oracle, W, 4, mode, (1, 2, 3), 0.5, 20.0)
+    _dense_one_step_vs_oracle(sq, oracle, w_c5b, 4, mode, (1, 2, 3), 0.5, 20.0, random_spec=(32768, 32768))
 
 
 def test_c5a_replica_batch_equals_oracle_chains(sq, oracle):

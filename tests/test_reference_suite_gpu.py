@@ -1,0 +1,30 @@
+"""The reference's own Python test-suite (sqaodpy/tests/*.py, unmodified), `sqaod.cuda` bound to libsqaod_b200.so -- once
+through the reference's CPython glue compiled unmodified against include/sqaodc/sqaodc.h, once through sqaod_b200.cext.
+The suite and the compiled glue are staged by `make -C oracle glue` (build container, /root/reference present) under
+oracle/_ref/refsuite, which is git-ignored and travels with the snapshot; without it the tests skip."""
+import os
+import re
+import subprocess
+import sys
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SUITE = os.path.join(ROOT, 'oracle', '_ref', 'refsuite')
+
+
+@pytest.mark.parametrize('binding', ['glue', 'cext'])
+def test_reference_python_suite(binding):
+    if not os.path.isdir(os.path.join(SUITE, 'tests')):
+        pytest.skip('oracle/_ref/refsuite not staged (run `make -C oracle glue` where /root/reference exists)')
+    if binding == 'glue' and not os.path.exists(os.path.join(SUITE, 'glue', 'cuda_dg_annealer.so')):
+        pytest.skip('reference glue not compiled')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'refsuite_runner.py'), binding], capture_output=True, text=True,
+                         timeout=1500, cwd=SUITE)
+    log = out.stdout[-6000:] + out.stderr[-2000:]
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(ROOT, 'gpurun_out', 'refsuite_%s.log' % binding), 'w') as f:
+        f.write(out.stdout + out.stderr)
+    m = re.search(r'(\d+) passed', out.stdout)
+    assert m and int(m.group(1)) > 100, log
+    assert 'REFSUITE_RC %s 0' % binding in out.stdout, log

@@ -45,5 +45,6 @@ if ann.get_sweep_mode() == 'field':
         print('%4d %d %8.1f %8.1f %8.1f %8.1f %8.1f %6d %6d' % (i, r[0], r[1] / mhz * 1e3, r[2] / mhz * 1e3, r[3] / mhz * 1e3, r[4] / mhz * 1e3, t_end[i] / 1e3, r[6], r[7]))
     for T in sorted(set(pc[:, 0].astype(int))):
         sel = pc[:, 0] == T
-        print('T=%d: %d CTAs, mean wait_fields %.1f us, wait_nb %.1f us, chain work %.1f us, loop %.1f us' % (
-            T, sel.sum(), pc[sel, 1].mean() / mhz * 1e3, pc[sel, 2].mean() / mhz * 1e3, pc[sel, 3].mean() / mhz * 1e3, pc[sel, 4].mean() / mhz * 1e3))
+        us = lambda k: pc[sel, k].mean() / mhz * 1e3
+        print('T=%d: %d CTAs, mean wait_fields %.1f us, wait_nb %.1f us, chain work %.1f us, loop %.1f us; neighbour warp waits: own chain %.1f us, tables %.1f us, remote words %.1f us (loop %.1f us); table warp: Philox %.1f us, masks %.1f us, waiting %.1f us' % (
+            T, sel.sum(), us(1), us(2), us(3), us(4), us(8), us(9), us(10), us(11), us(12), us(13), us(14)))

@@ -93,7 +93,7 @@ int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int d
  * [11] evaluation passes, [12] / [13] gather waits forced by an uncertain attempt / by a second commit, [14] passes that
  * ended on a blocked attempt */
 int sqb_dg_annealer_get_profile(sqb_handle ann, unsigned long long *out16, int dtype);
-/* field mode, last launch, chain warp 0 of every CTA (8 words per CTA): trotters, cycles waiting for fields / for neighbour CTAs,
+/* field mode, last launch, chain warp 0 of every CTA (16 words per CTA; words 8-11: the neighbour warp): trotters, cycles waiting for fields / for neighbour CTAs,
  * cycles of chain work, cycles of the whole sweep loop, end time (globaltimer ns), accepted flips of that warp, evaluation passes */
 int sqb_dg_annealer_get_cta_profile(sqb_handle ann, unsigned long long *out, int max_ctas, int *n, int dtype);
 /* how annealOneStep obtains h_x + sum_j J_xj q_j (no reference counterpart; both modes run the same Markov chain):

@@ -124,6 +124,7 @@ private:
     bool fieldMode_ = false;
     bool specChain_ = true;        /* window-parallel accept chain (SQAOD_B200_SWEEP_SPEC=0: the sequential per-round chain) */
     DevBuf<real> dF_;              /* [m * replicas][ldJ] fields at step start */
+    DevBuf<unsigned char> dTables_; /* field mode: per-step tables of the sweep (sweepTablesKernel) */
     DevBuf<real> dRowMax_;         /* scratch of prepare(): max_j |J[i][j]| per row */
     real jAbsMax_ = real(0);       /* max |J| (field mode: bound of a cross term in flight) */
     bool fieldsHaveH_ = false;     /* dF_ holds h + 2 J.q (written back by a sweep) instead of the spin GEMM's J.q */

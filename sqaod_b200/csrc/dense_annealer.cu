@@ -99,6 +99,9 @@ template <class real> struct SweepParams {
      * step start (spin GEMM or the previous step's write-back); kept in shared memory and updated incrementally by the sweep */
     real *F;
     int ldF, writeBackF;
+    /* field mode: per (replica of the launch, CTA, window) record of Philox draws and conflict masks, written by
+     * sweepTablesKernel before the sweep (SweepTabRec layout) */
+    const unsigned char *tables;
     real uncBound;   /* field mode: 4 scaleA max|J| (with slack) -- bounds the cross term of a gather that is still in flight */
     int fieldHasH;   /* field mode: the rows in F already hold h + 2 J.q (written back by the previous step) instead of J.q */
     int specChain; /* accept chain evaluates a whole window in parallel and commits flips in order (see the chain warp) */
@@ -107,7 +110,7 @@ template <class real> struct SweepParams {
 
 /* shared-memory carve-up, identical on host and device */
 template <class real> struct SweepSmem {
-    size_t field, ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, xn, conf, confAny, accLog, sgnLog, spec, carry, pend, cstate, flipQ, counter, total;
+    size_t field, ring, bars, qcur, qsnap, nbsnap, dots, cross, xs, xb, us, hs, need, xn, conf, confAny, accLog, sgnLog, spec, carry, pend, cstate, flipQ, counter, total;
     int flipQLen;
     /* fieldElems > 0: field mode -- T rows of fieldElems local fields instead of the TMA ring (stages == 0) */
     __host__ __device__ SweepSmem(int T, int nw64, int chunkElems, int stages, int K, int dotWarps, int fieldElems = 0) {
@@ -127,6 +130,7 @@ template <class real> struct SweepSmem {
         o = (o + 15) & ~(size_t)15;
         us = o; o += tab * T * K * sizeof(real);
         hs = o; o += (fieldElems ? 0 : tab) * T * K * sizeof(real); /* field mode keeps h inside its field rows */
+        need = o; o += (fieldElems ? tab : 0) * T * K * 4;          /* field mode: local-neighbour conflict masks from the table pre-pass */
         xn = o; o += (size_t)2 * tab * K * 4;
         conf = o; o += tab * 2 * K * 4;      /* [tab][2 sides][K] */
         confAny = o; o += tab * 2 * 4 * 2;   /* [tab][2 sides] + pubMask[tab][2 sides] */
@@ -276,6 +280,128 @@ __device__ __forceinline__ int sweepPhase(int y, int m) { /* 0: even, 1: trotter
     return ((m & 1) && y == m - 1) ? 1 : 0;
 }
 
+/* ---------------- field mode: table pre-pass ----------------
+ * Everything about a step that depends on the Philox stream only -- which spin each attempt draws, -ln(u), and which attempts
+ * of neighbouring trotters draw the same spin index within the look-back range -- is computed for ALL windows of the step by
+ * one throughput kernel before the sweep (one warp per CTA-window, every SM busy), instead of by one latency-bound helper warp
+ * per sweep CTA that had to keep three windows ahead of the accept chain (it took 3.7 us per 16-round window and paced the
+ * whole sweep).  The sweep kernel's table warp only copies one ~1 KB record per window into shared memory. */
+template <class real> struct SweepTabRec { /* byte offsets inside the record of one (CTA, window); arrays are [maxT][K] / [2 sides][K] */
+    size_t xs, xb, us, need, xn, conf, misc, bytes;
+    __host__ __device__ SweepTabRec(int maxT, int K) {
+        size_t o = 0;
+        xs = o; o += (size_t)maxT * K * 4;
+        xb = o; o += (size_t)maxT * K * 4;
+        need = o; o += (size_t)maxT * K * 4;
+        xn = o; o += (size_t)2 * K * 4;
+        conf = o; o += (size_t)2 * K * 4;
+        misc = o; o += 16; /* confAny[2], pubMask[2] */
+        us = o; o += (size_t)maxT * K * sizeof(real);
+        bytes = (o + 15) & ~(size_t)15;
+    }
+};
+
+struct SweepTabParams {
+    unsigned char *tables;
+    int N, m, G, K, nW, replicaBase;
+    unsigned long long seed, step;
+    int sqa;
+};
+
+template <class real> __global__ void __launch_bounds__(128) sweepTablesKernel(const SweepTabParams P) {
+    extern __shared__ int tabScratch[]; /* per warp: own draws [maxT][K], then the foreign neighbours' draws [2 sides][3 windows][K] */
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * 4 + wib, cta = blockIdx.y, rp = blockIdx.z;
+    if (w >= P.nW) return;
+    const int N = P.N, m = P.m, G = P.G, K = P.K;
+    const int baseT = m / G, remT = m % G;
+    const int T = baseT + (cta < remT ? 1 : 0), maxT = baseT + (remT ? 1 : 0);
+    const int y0 = cta * baseT + min(cta, remT);
+    const unsigned long long seedR = P.seed + (unsigned long long)(P.replicaBase + rp);
+    const SweepTabRec<real> R(maxT, K);
+    unsigned char *rec = P.tables + (((size_t)rp * G + cta) * P.nW + w) * R.bytes;
+    int *rxs = reinterpret_cast<int *>(rec + R.xs), *rxb = reinterpret_cast<int *>(rec + R.xb), *rxn = reinterpret_cast<int *>(rec + R.xn);
+    uint32_t *rneed = reinterpret_cast<uint32_t *>(rec + R.need), *rconf = reinterpret_cast<uint32_t *>(rec + R.conf), *rmisc = reinterpret_cast<uint32_t *>(rec + R.misc);
+    real *rus = reinterpret_cast<real *>(rec + R.us);
+    int *sx = tabScratch + (size_t)wib * (maxT * K + 6 * K);
+    int *snb = sx + maxT * K;
+    const int Kw = min(K, N - w * K);
+    auto roundsIn = [&](int ww) { return min(K, N - ww * K); };
+    const uint32_t kM = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
+
+    for (int idx = lane; idx < T * K; idx += 32) { /* own draws */
+        const int t = idx / K, r = idx % K;
+        int x = -1 - idx;
+        if (r < Kw) {
+            const Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(w * K + r), (uint32_t)(y0 + t));
+            x = (int)(p.w[0] % (uint32_t)N);
+            int w64, bit;
+            spinBitPos(x, w64, bit);
+            rxs[t * K + r] = x;
+            rxb[t * K + r] = ((2 * w64 + (bit >> 5)) << 5) | (bit & 31);
+            rus[t * K + r] = negLogUniform<real>(p);
+        }
+        sx[idx] = x;
+    }
+    const bool remote = P.sqa && G > 1;
+    const int yLeft = (y0 == 0) ? m - 1 : y0 - 1, yRight = (y0 + T - 1 == m - 1) ? 0 : y0 + T;
+    if (remote) { /* the foreign neighbours' draws of windows w-1, w, w+1 */
+        for (int idx = lane; idx < 6 * K; idx += 32) {
+            const int side = idx / (3 * K), u = (idx / K) % 3, j = idx % K;
+            const int wu = w - 1 + u;
+            int x = -100 - idx;
+            if (wu >= 0 && wu < P.nW && j < roundsIn(wu)) {
+                const Philox4 p = sqbPhilox(seedR, P.step, DOM_DENSE_SWEEP, (uint32_t)(wu * K + j), (uint32_t)(side ? yRight : yLeft));
+                x = (int)(p.w[0] % (uint32_t)N);
+            }
+            snb[idx] = x;
+            if (u == 1 && j < Kw) rxn[side * K + j] = x;
+        }
+    }
+    __syncwarp();
+    /* local neighbours: rounds of trotter t-1 / t+1 (same CTA) that must be final before round r of trotter t -- same spin
+     * index, earlier in the reference order (earlier round, or same round and earlier phase) */
+    for (int idx = lane; idx < T * K; idx += 32) {
+        const int t = idx / K, r = idx % K;
+        uint32_t nd = 0u;
+        if (P.sqa && r < Kw) {
+            const int x = sx[idx];
+            const int g = y0 + t, ph = sweepPhase(g, m);
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const int gn = side ? (g == m - 1 ? 0 : g + 1) : (g == 0 ? m - 1 : g - 1);
+                if (gn < y0 || gn >= y0 + T) continue;
+                const int tn = gn - y0;
+                uint32_t msk = 0u;
+                for (int j = 0; j < Kw; ++j) msk |= (sx[tn * K + j] == x ? 1u : 0u) << j;
+                msk &= ((1u << r) - 1u) | ((sweepPhase(gn, m) < ph ? 1u : 0u) << r);
+                nd |= msk << (16 * side);
+            }
+        }
+        if (r < Kw) rneed[idx] = nd;
+    }
+    if (remote) { /* foreign neighbours: conf = their attempts of windows w-1 / w on my edge trotter's spin index; pubMask = rounds
+                   * whose accept flag they can ever read (their attempts of windows w / w+1 draw the same index) */
+        uint32_t anyMine = 0u, pubMine = 0u; /* K <= 16: lane = (side, r) */
+        const int side = lane / K, r = lane % K;
+        if (side < 2 && r < Kw) {
+            uint32_t mP = 0u, mC = 0u, mQ = 0u;
+            const int xe = sx[(side ? T - 1 : 0) * K + r];
+            const int *nb = snb + side * 3 * K;
+            for (int j = 0; j < K; ++j) {
+                mP |= (nb[j] == xe ? 1u : 0u) << j;
+                mC |= (nb[K + j] == xe ? 1u : 0u) << j;
+                mQ |= (nb[2 * K + j] == xe ? 1u : 0u) << j;
+            }
+            rconf[side * K + r] = mP | (mC << K);
+            anyMine = (mP | mC) ? 1u : 0u;
+            pubMine = (mC | mQ) ? 1u : 0u;
+        }
+        const uint32_t nz = __ballot_sync(0xffffffffu, anyMine != 0u), pb = __ballot_sync(0xffffffffu, pubMine != 0u);
+        if (lane < 2) { rmisc[lane] = (nz >> (lane * K)) & kM; rmisc[2 + lane] = (pb >> (lane * K)) & kM; }
+    } else if (lane < 4) rmisc[lane] = 0u;
+}
+
 template <class real, bool SQA, int K, bool FIELD>
 __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepParams<real> P) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -325,6 +451,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     int *xb = reinterpret_cast<int *>(smem + L.xb);          /* [3][maxT][K]: (32-bit word index << 5) | bit of spin x in a packed row */
     real *us = reinterpret_cast<real *>(smem + L.us);
     real *hs = reinterpret_cast<real *>(smem + L.hs);
+    uint32_t *need = reinterpret_cast<uint32_t *>(smem + L.need); /* FIELD: [TAB][maxT][K]: lo 16 bits left neighbour, hi 16 right */
     real *carry = reinterpret_cast<real *>(smem + L.carry);  /* FIELD: [maxT][K] */
     real *pend = reinterpret_cast<real *>(smem + L.pend);    /* FIELD: [maxT][32] */
     unsigned char *cstate = smem + L.cstate;                 /* FIELD: [maxT][8 * sizeof(real)] */
@@ -384,6 +511,30 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 xn[(side * TAB + slot) * K + rl] = (int)(p.w[0] % (uint32_t)N);
             }
         }
+    };
+
+    /* field mode: the tables of window w come from the pre-pass (sweepTablesKernel); copy the record into table slot w & (TAB-1) */
+    auto loadWindow = [&](int w, int t0, int nthr) {
+        if (w >= nW) return;
+        const SweepTabRec<real> R(maxT, K);
+        const unsigned char *rec = P.tables + (((size_t)blockIdx.y * G + cta) * nW + w) * R.bytes;
+        const int slot = w & (TAB - 1);
+        const int nTK = maxT * K;
+        const int *gxs = reinterpret_cast<const int *>(rec + R.xs), *gxb = reinterpret_cast<const int *>(rec + R.xb), *gxn = reinterpret_cast<const int *>(rec + R.xn);
+        const uint32_t *gneed = reinterpret_cast<const uint32_t *>(rec + R.need), *gconf = reinterpret_cast<const uint32_t *>(rec + R.conf);
+        const uint32_t *gmisc = reinterpret_cast<const uint32_t *>(rec + R.misc);
+        const real *gus = reinterpret_cast<const real *>(rec + R.us);
+        for (int i = t0; i < nTK; i += nthr) {
+            xs[slot * nTK + i] = __ldcg(gxs + i);
+            xb[slot * nTK + i] = __ldcg(gxb + i);
+            need[slot * nTK + i] = __ldcg(gneed + i);
+            us[slot * nTK + i] = __ldcg(gus + i);
+        }
+        for (int i = t0; i < 2 * K; i += nthr) {
+            xn[((i / K) * TAB + slot) * K + (i % K)] = __ldcg(gxn + i);
+            conf[slot * 2 * K + i] = __ldcg(gconf + i);
+        }
+        if (t0 < 2) { confAny[slot * 2 + t0] = __ldcg(gmisc + t0); pubMask[slot * 2 + t0] = __ldcg(gmisc + 2 + t0); }
     };
 
     unsigned long long nWaits = 0;
@@ -508,10 +659,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             atomicOr(&dst[w64], (unsigned long long)nib << bit);
         }
     }
-    prepWindow(0, tid, SW_THREADS);
-    prepWindow(1, tid, SW_THREADS);
-    prepWindow(2, tid, SW_THREADS);
-    if (FIELD) prepWindow(3, tid, SW_THREADS);
+    if (FIELD) { for (int w0 = 0; w0 < 4; ++w0) loadWindow(w0, tid, SW_THREADS); }
+    else { prepWindow(0, tid, SW_THREADS); prepWindow(1, tid, SW_THREADS); prepWindow(2, tid, SW_THREADS); }
     real *const Fg = FIELD ? P.F + ((size_t)replica * m + y0) * P.ldF : NULL; /* this CTA's rows of the field matrix */
     if (FIELD) { /* the field rows in shared memory hold H[t][j] = h[j] + 2 sum_i J[j][i] q_t[i]; ldF is a multiple of 128 elements */
         if (P.fieldHasH) {
@@ -529,8 +678,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     __syncthreads();
     if (!FIELD) for (int i = tid; i < T * NW; i += SW_THREADS) qsnap[i] = qcur[i];
     for (int i = tid; i < 2 * NW; i += SW_THREADS) nbsnap[2 * NW + i] = nbsnap[i]; /* windows 0 and 1 both start from S_0 */
-    if (warp == (FIELD ? (int)SW_FIELD_NB_WARP : (int)SW_NB_WARP)) { /* conflict masks of the windows whose successor's tables exist */
-        constexpr int PW = FIELD ? 4 : 3;
+    if (!FIELD && warp == SW_NB_WARP) { /* conflict masks of the windows whose successor's tables exist (field mode: from the pre-pass) */
+        constexpr int PW = 3;
         for (int v = 0; v < PW - 1; ++v) maskWindow(v);
         if (nW <= PW) maskWindow(PW - 1);
     }
@@ -869,24 +1018,45 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         }
     } else if (nbWarp) {
         /* the neighbours' S_{wn-1} and the conflict masks of window wn, into the buffers window wn-2 has finished with */
+        long long nbW0 = 0, nbW1 = 0, nbW2 = 0;
         for (int wn = 1; wn < nW; ++wn) {
+            const long long a0 = waited;
             waitCount(aReplayDone, (uint32_t)(wn - 1), 20);
-            waitCount(aPrepCount, (uint32_t)min(wn + 2, nW), 20); /* the publish mask looks at the neighbour's next window too */
+            const long long a1 = waited;
+            waitCount(aPrepCount, (uint32_t)min(wn + 2, nW), 20); /* the conflict masks of window wn are in place (the chain reads them) */
+            const long long a2 = waited;
             neighbourWindow(wn);
+            nbW0 += a1 - a0; nbW1 += a2 - a1; nbW2 += waited - a2;
             signalCount(aNbCount, (uint32_t)wn + 1u);
+        }
+        if (FIELD && P.stats && lane == 0 && blockIdx.y == 0) { /* per-CTA profile: the neighbour warp's waits (own chain, tables, remote words) */
+            unsigned long long *pc = P.stats + 16 + 16 * (size_t)cta;
+            pc[8] = (unsigned long long)nbW0; pc[9] = (unsigned long long)nbW1; pc[10] = (unsigned long long)nbW2;
+            pc[11] = (unsigned long long)(clock64() - tLoop0);
         }
     } else if (prepWarp) {
         /* tables of window wp go to the slot of window wp-4, dead once S_{wp-2} is built (window wp-3 replayed) */
+        long long prepT0 = 0, prepT1 = 0;
         for (int wp = FIELD ? 4 : 3; wp < nW; ++wp) {
             /* field mode: eight slots, one more window of look-ahead (the dot warps still read window wp-4's slot then) */
             if (FIELD) waitCount(aReplayDone, (uint32_t)wp - 3u, 20); /* window wp-4 replayed: the slot of window wp-8 is dead */
             else waitCount(aSnapCount, (uint32_t)wp - 1u, 20);
             if (!FIELD && remote) waitCount(aNbCount, (uint32_t)wp - 1u, 20); /* the neighbour warp reads window wp-4's draws for window wp-2 */
-            prepWindow(wp, lane, 32);
+            const long long c0 = clock64();
+            if (FIELD) loadWindow(wp, lane, 32); /* one record of the table pre-pass */
+            else prepWindow(wp, lane, 32);
             __syncwarp();
-            maskWindow(wp - 1); /* the conflict masks look one window ahead */
-            if (wp == nW - 1) maskWindow(wp);
+            const long long c1 = clock64();
+            if (!FIELD) {
+                maskWindow(wp - 1); /* the conflict masks look one window ahead */
+                if (wp == nW - 1) maskWindow(wp);
+            }
+            prepT0 += c1 - c0; prepT1 += clock64() - c1;
             signalCount(aPrepCount, (uint32_t)wp + 1u);
+        }
+        if (FIELD && P.stats && lane == 0 && blockIdx.y == 0) { /* per-CTA profile: cycles in the Philox tables / the conflict masks / waiting */
+            unsigned long long *pc = P.stats + 16 + 16 * (size_t)cta;
+            pc[12] = (unsigned long long)prepT0; pc[13] = (unsigned long long)prepT1; pc[14] = (unsigned long long)waited;
         }
     } else if (FIELD && chainWarp) {
         /* ---------------- field mode: the accept chain, one warp per trotter, a whole window evaluated at once ----------------
@@ -935,28 +1105,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
         const bool haveT = fast && (cw < T);
         const uint32_t infoF = haveT ? tinfo[tF] : 0u;
         const int phF = (int)(infoF & 3u), tnLF = (int)((infoF >> 2) & 63u) - 1, tnRF = (int)((infoF >> 8) & 63u) - 1;
-        /* does the attempt of the local left / right neighbour in the SAME round come before mine? */
-        const bool precLF = haveT && tnLF >= 0 && (int)(tinfo[tnLF] & 3u) < phF, precRF = haveT && tnRF >= 0 && (int)(tinfo[tnRF] & 3u) < phF;
         const bool edgeLF = haveT && remote && tnLF < 0, edgeRF = haveT && remote && tnRF < 0;
         uint32_t pwF = 0u, pr0F = 0u;   /* pending generation of gathers: window it was issued in + 1 (0: none), its round */
         real pSF = real(0), carryN = real(0); /* its signed scale; lanes K..2K-1: corrections known so far for the next window's rounds */
-        uint32_t needNext = 0u;         /* lane (side, r): rounds of the local neighbour `side` that must be final before round r of the coming window */
-        auto localNeed = [&](int wq) -> uint32_t { /* 16 lane-addressed shuffles instead of K x K shared-memory compares */
-            const int Kq = roundsIn(wq), sq_ = wq & (TAB - 1);
-            const int tn = (hI == 0) ? tnLF : tnRF;
-            const int xm = xs[(sq_ * maxT + tF) * K + rI];
-            const int xnb = (hI < 2 && tn >= 0 && rI < Kq) ? xs[(sq_ * maxT + tn) * K + rI] : -1 - lane;
-            uint32_t msk = 0u;
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                const int got = __shfl_sync(0xffffffffu, xnb, (lane - rI) + j);
-                msk |= (got == xm ? 1u : 0u) << j;
-            }
-            const bool prec = (hI == 0) ? precLF : precRF;
-            msk &= ((1u << rI) - 1u) | ((prec ? 1u : 0u) << rI);
-            return (hI < 2 && tn >= 0 && rI < Kq) ? msk : 0u;
-        };
-        if (SQA && haveT) needNext = localNeed(0);
 
         for (int w = 0; w < nW; ++w) {
             const int Kw = roundsIn(w), KwN = (w + 1 < nW) ? roundsIn(w + 1) : 0;
@@ -990,9 +1141,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                 const int xGather = (hI == 0) ? xMine : ((hI == 1 && rI < KwN) ? xs[(slotN * maxT + t) * K + rI] : -1);
                 uint32_t needL = 0u, needR = 0u, cmL = 0u, cmR = 0u;
                 if (SQA) {
-                    needL = needNext; /* lanes 0..K-1 hold the left masks, lanes K..2K-1 the right ones */
-                    needR = __shfl_down_sync(0xffffffffu, needNext, K);
-                    if (hI != 0) { needL = 0u; needR = 0u; }
+                    if (hI == 0 && rI < Kw) { /* local neighbours (table pre-pass): their earlier attempts on my spin index */
+                        const uint32_t nd = need[o];
+                        needL = nd & 0xffffu; needR = nd >> 16;
+                    }
                     if (hI == 0 && rI < Kw) { /* neighbours owned by other CTAs: attempts of theirs that precede mine on the same spin index */
                         const uint32_t precBase = (w > 0 ? kMask : 0u) | (((1u << rI) - 1u) << K);
                         if (edgeLF) cmL = conf[(slot * 2 + 0) * K + rI] & (precBase | (((nbPhaseL < phF) ? 1u : 0u) << (K + rI)));
@@ -1119,7 +1271,6 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                     stRelaxed(sBits + ((size_t)(y0 + t) * SW_SNAP_SLOTS + (size_t)(w % SW_SNAP_SLOTS)) * NW,
                               ((P.snapBase + (unsigned long long)w + 1ull) << 16) | (unsigned long long)accC);
                 (void)sgnC;
-                if (SQA && w + 1 < nW) needNext = localNeed(w + 1); /* while the slower trotters of the CTA finish the window */
                 cycEnd += clock64() - tw2;
             }
             } else {
@@ -1136,19 +1287,6 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                     const int o = (buf * maxT + t) * K + rI;
                     dots[o] += carry[t * K + rI];
                     carry[t * K + rI] = real(0);
-                }
-                if (SQA) { /* rounds of a local neighbour that draw the same spin index: my draws in lanes 0..K-1, the neighbour's in lanes K..2K-1, one MATCH */
-                    const uint32_t info = tinfo[t];
-                    const int xMine = (hI == 0 && rI < Kw) ? xs[(slot * maxT + t) * K + rI] : -1 - lane;
-#pragma unroll
-                    for (int side = 0; side < 2; ++side) {
-                        const int tn = (int)((info >> (2 + 6 * side)) & 63u) - 1;
-                        if (tn >= 0) { /* warp-uniform */
-                            const int v = (hI == 1 && rI < Kw) ? xs[(slot * maxT + tn) * K + rI] : xMine;
-                            const uint32_t mm = __match_any_sync(0xffffffffu, v);
-                            if (hI == 0) lconf[(t * 2 + side) * K + rI] = (rI < Kw) ? ((mm >> K) & kMask) : 0u;
-                        } else if (hI == 0) lconf[(t * 2 + side) * K + rI] = 0u;
-                    }
                 }
                 if (lane == 0) { cs[2] = 0u; cs[3] = 0u; }
             }
@@ -1185,14 +1323,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                                 const int tn = (int)((info >> (2 + 6 * side)) & 63u) - 1;
                                 uint32_t nbit;
                                 if (tn >= 0) {
-                                    const uint32_t lm = lconf[(t * 2 + side) * K + rI];
-                                    if (lm) { /* rare: the neighbour draws this spin index in this window too */
-                                        const uint32_t need = lm & (((1u << rI) - 1u) | ((((int)(tinfo[tn] & 3u) < ph) ? 1u : 0u) << rI));
-                                        if (need) { /* its earlier attempts on this index must be final: frontier first, spin word after */
-                                            const uint32_t fn = ldAcquireCta(aFront + 4u * (uint32_t)tn) - wBase;
-                                            const uint32_t fin = (fn >= 32u) ? 0xffffffffu : ((1u << fn) - 1u);
-                                            if (need & ~fin) blk = true;
-                                        }
+                                    const uint32_t ndm = (need[o] >> (16 * side)) & 0xffffu; /* table pre-pass: its earlier attempts on this spin index */
+                                    if (ndm) { /* rare: they must be final -- frontier first, spin word after */
+                                        const uint32_t fn = ldAcquireCta(aFront + 4u * (uint32_t)tn) - wBase;
+                                        const uint32_t fin = (fn >= 32u) ? 0xffffffffu : ((1u << fn) - 1u);
+                                        if (ndm & ~fin) blk = true;
                                     }
                                     nbit = (ldsU32(aMy0 + (uint32_t)tn * rowBytes + aw) >> bit) & 1u;
                                 } else {
@@ -1333,7 +1468,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             }
             if (lane == 0 && cw != 0) atomicAdd(P.stats + 15, (unsigned long long)cycBar); /* chain warps 1..3: cycles waiting in the window barrier */
             if (lane == 0 && cw == 0 && blockIdx.y == 0) { /* per-CTA profile of the last launch (chain warp 0) */
-                unsigned long long *pc = P.stats + 16 + 8 * (size_t)cta;
+                unsigned long long *pc = P.stats + 16 + 16 * (size_t)cta;
                 unsigned long long gt;
                 asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
                 pc[0] = (unsigned long long)T; pc[1] = (unsigned long long)waitedRows; pc[2] = (unsigned long long)waitedNbF;
@@ -2100,7 +2235,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
         if (fieldRefreshWanted_ > 0) fieldRefresh_ = fieldRefreshWanted_;
     }
     allocHandoff();
-    dStats_.alloc(dev_, 16 + 8 * (size_t)dev_->numSMs());
+    dStats_.alloc(dev_, 16 + 16 * (size_t)dev_->numSMs());
     launchCount_ = 0;
     CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(true, K_, fieldMode_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
     CUDA_CHECK(cudaFuncSetAttribute(sweepKernelFor<real>(false, K_, fieldMode_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_));
@@ -2306,9 +2441,24 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
     void *args[] = {&P};
     const void *fn = sweepKernelFor<real>(sqa, K_, fieldMode_);
     dev_->makeCurrent();
+    P.tables = NULL;
     for (int base = 0; base < nReplicas_; base += replicasPerLaunch_) {
         P.replicaBase = base;
         const int nr = std::min(replicasPerLaunch_, nReplicas_ - base);
+        if (fieldMode_) { /* table pre-pass for the replicas of this launch (Philox draws, -ln u, conflict masks of every window) */
+            const int maxT = (m_ + grid_ - 1) / grid_;
+            const SweepTabRec<real> R(maxT, K_);
+            const size_t need = R.bytes * (size_t)nWindows_ * grid_ * replicasPerLaunch_;
+            if (dTables_.n < need) dTables_.alloc(dev_, need);
+            SweepTabParams TP;
+            TP.tables = dTables_.p; TP.N = N_; TP.m = m_; TP.G = grid_; TP.K = K_; TP.nW = nWindows_; TP.replicaBase = base;
+            TP.seed = seed_; TP.step = step_; TP.sqa = sqa ? 1 : 0;
+            const size_t scratch = (size_t)4 * (maxT * K_ + 6 * K_) * sizeof(int);
+            sweepTablesKernel<real><<<dim3((nWindows_ + 3) / 4, grid_, nr), 128, scratch, dev_->stream()>>>(TP);
+            CUDA_CHECK(cudaGetLastError());
+            ++dev_->launchCount;
+            P.tables = dTables_.p;
+        }
         CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid_, nr), dim3(SW_THREADS), args, smemBytes_, dev_->stream()));
         ++dev_->launchCount;
     }
@@ -2461,7 +2611,7 @@ template <class real> void B200DenseGraphAnnealer<real>::getCounters(unsigned lo
 template <class real> int B200DenseGraphAnnealer<real>::getCtaProfile(unsigned long long *out, int maxCtas) const {
     const int n = std::min(maxCtas, std::min(grid_, dev_->numSMs()));
     if (dStats_.p && n > 0) {
-        dev_->d2h(out, dStats_.p + 16, (size_t)n * 8 * sizeof(unsigned long long));
+        dev_->d2h(out, dStats_.p + 16, (size_t)n * 16 * sizeof(unsigned long long));
         dev_->synchronize();
     }
     return n;

@@ -233,7 +233,7 @@ class DenseGraphAnnealer(_SolverBase):
 
     def get_cta_profile(self):
         """per-CTA profile of the last field-mode sweep: array (n_ctas, 8), see sqb_dg_annealer_get_cta_profile"""
-        out = np.zeros((512, 8), np.uint64); n = C.c_int(0)
+        out = np.zeros((512, 16), np.uint64); n = C.c_int(0)
         _lib.check(L.sqb_dg_annealer_get_cta_profile(self._cobj, ptr(out), 512, C.byref(n), self._dt))
         return out[:n.value]
 

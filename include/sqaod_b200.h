@@ -88,6 +88,9 @@ int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, 
  * [3] chain-warp busy cycles, [5] helper-warp busy cycles (snapshots, conflict masks), [6] prep-warp busy cycles (Philox
  * tables), [4] / [7] chain-warp cycles waiting for dot products / for neighbour data */
 int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int dtype);
+/* field mode with carried fields (field_refresh > 1): H[y][j] = h[j] + 2 sum_i J[j][i] q[y][i] as the sweep left it, rows of ldH
+ * elements; *valid = 0 when the solver carries no fields (classic mode, per-step recomputation, spins just written) */
+int sqb_dg_annealer_get_fields(sqb_handle ann, void *H, int ldH, int *valid, int dtype);
 /* the eight counters above plus the field-mode chain profile of chain warp 0, summed over CTAs: [8] cycles waiting for
  * cross-term gathers, [9] cycles idle (blocked on another warp / CTA), [10] cycles in the per-window barrier of the chain warps,
  * [11] evaluation passes, [12] / [13] gather waits forced by an uncertain attempt / by a second commit, [14] passes that

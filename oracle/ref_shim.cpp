@@ -1,6 +1,6 @@
 /* oracle/ref_shim.cpp -- TEST INFRASTRUCTURE.  C entry points over the two Eigen-free reference
  * translation units that can be compiled where they lie (sqaodc/common/Random.cpp,
- * sqaodc/cpu/Dot_SIMD.cpp).  Used by tests/test_oracle_ref.py to pin the oracle's MT19937 stream
+ * sqaodc/cpu/Dot_SIMD.cpp).  Used by tests/test_oracle_rng.py to pin the oracle's MT19937 stream
  * and AVX2 dot product against the reference's own object code.  Built only when /root/reference
  * exists (oracle/Makefile target `ref`); output goes to oracle/_ref/ (git-ignored). */
 #include <sqaodc/common/Random.h>

@@ -57,3 +57,12 @@ def simple(prefix, name):
         check(fn(h(obj), dt(dtype)))
     call.__name__ = name
     return call
+
+
+def vec(a):
+    """a vector argument as the reference glue accepts it (NpVectorType, pyglue/pyglue.h:112-131): 1-D, or 2-D with one row or
+    one column"""
+    a = np.asarray(a)
+    if a.ndim >= 3 or (a.ndim == 2 and a.shape[0] != 1 and a.shape[1] != 1):
+        raise RuntimeError('ndarray is not 1-diemsional.')
+    return np.ascontiguousarray(a.reshape(-1))

@@ -1,7 +1,7 @@
 """cuda_bg_annealer (method table: sqaodc/pyglue/annealer.inc:884-910, bipartite-graph variant)"""
 import ctypes as C
 import numpy as np
-from ._glue import L, check, ptr, dt, h, new_handle, stride, simple
+from ._glue import L, check, ptr, dt, h, new_handle, stride, simple, vec
 from . import _glue
 
 _P = 'bg_annealer'
@@ -79,7 +79,7 @@ def get_q(obj, dtype):
 
 
 def set_q(obj, qpair, dtype):
-    q0, q1 = qpair
+    q0, q1 = vec(qpair[0]), vec(qpair[1])
     check(L.sqb_bg_annealer_set_q(h(obj), ptr(q0), ptr(q1), q0.shape[0], q1.shape[0], dt(dtype)))
 
 

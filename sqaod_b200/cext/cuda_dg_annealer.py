@@ -1,7 +1,7 @@
 """cuda_dg_annealer (method table: sqaodc/pyglue/annealer.inc:884-910, dense-graph variant)"""
 import ctypes as C
 import numpy as np
-from ._glue import L, check, ptr, dt, h, new_handle, stride, simple
+from ._glue import L, check, ptr, dt, h, new_handle, stride, simple, vec
 from . import _glue
 
 _P = 'dg_annealer'
@@ -79,6 +79,7 @@ def get_q(obj, dtype):
 
 
 def set_q(obj, q, dtype):
+    q = vec(q)
     check(L.sqb_dg_annealer_set_q(h(obj), ptr(q), q.shape[0], dt(dtype)))
 
 

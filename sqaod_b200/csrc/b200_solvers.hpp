@@ -124,6 +124,7 @@ private:
     bool fieldMode_ = false;
     bool specChain_ = true;        /* window-parallel accept chain (SQAOD_B200_SWEEP_SPEC=0: the sequential per-round chain) */
     DevBuf<real> dF_;              /* [m * replicas][ldJ] fields at step start */
+    AsyncReadback<real> eBack_;     /* energies: pinned landing buffer + completion event (calculate_E never synchronises the stream) */
     DevBuf<unsigned char> dTables_; /* field mode: per-step tables of the sweep (sweepTablesKernel) */
     DevBuf<real> dRowMax_;         /* scratch of prepare(): max_j |J[i][j]| per row */
     real jAbsMax_ = real(0);       /* max |J| (field mode: bound of a cross term in flight) */
@@ -137,6 +138,7 @@ public:
     /* mode -1: automatic (field mode whenever the field rows fit in shared memory), 0: classic (one J row per attempt),
      * 1: field mode (error in prepare() when it does not fit); fieldRefresh > 0: steps between two J.q recomputations */
     void setSweepMode(int mode, int fieldRefresh);
+    bool getFields(real *H, int ldH) const; /* carried local fields h + 2 J.q (field mode with write-back), [rows][ldH] */
 private:
     size_t smemBytes_;
     mutable unsigned long long lastBarrierWaitDot_ = 0, lastBarrierWaitChain_ = 0;

@@ -298,6 +298,7 @@ public:
         ddE_.alloc(dev_, (size_t)m_ * ldc_);
         dE_.alloc(dev_, m_);
         E_.resize(m_);
+        eBack_.alloc(dev_, m_);
         hq0_.assign((size_t)m_ * ldq0_, 0);
         hq1_.assign((size_t)m_ * ldq1_, 0);
         xPairs_.clear();
@@ -344,6 +345,7 @@ public:
     }
     const HostVector &get_E() const {
         if (!this->isEAvailable()) const_cast<This *>(this)->calculate_E();
+        const_cast<This *>(this)->eBack_.wait(const_cast<This *>(this)->E_.data, (size_t)m_);
         return E_;
     }
     const sq::BitSetPairArray &get_x() const {
@@ -364,6 +366,7 @@ public:
     real getSystemE(real G, real beta) const {
         This *self = const_cast<This *>(this);
         self->calculateEnergy();
+        self->eBack_.wait(self->E_.data, (size_t)m_);
         real E = E_.sum() / m_;
         if (sq::isSQAAlgorithm(algo_)) {
             real spinDotSum = (real)(ringSpinDot(*dev_, dq0_.p, ldq0_, N0_, m_) + ringSpinDot(*dev_, dq1_.p, ldq1_, N1_, m_));
@@ -399,8 +402,7 @@ private:
         }
         if (!done)
             devBatchedEnergy<real>(*dev_, dE_.p, dJ_.p, ldJ_, N1_, N0_, dq0_.p, ldq0_, dq1_.p, ldq1_, dh1_.p, dh0_.p, m_, -sign, -sign * c_);
-        dev_->d2h(E_.data, dE_.p, sizeof(real) * m_);
-        dev_->synchronize();
+        eBack_.enqueue(dE_.p, (size_t)m_); /* asynchronous: get_E() waits for this copy's own event */
         this->setState(Base::solEAvailable);
     }
     void halfStep(int side, bool sqa, real twoDivM, real coef, real beta) {
@@ -464,6 +466,7 @@ private:
 
     B200Device *dev_;
     DevBuf<real> dJ_, dJT_, dh0_, dh1_, ddE_, dE_;
+    AsyncReadback<real> eBack_; /* energies: pinned landing buffer + completion event */
     DevBuf<signed char> dq0_, dq1_;
     int ldJ_, ldJT_, ldq0_, ldq1_, ldc_;
     real c_;

@@ -2,6 +2,7 @@
  * Thin: maps plain buffers onto sqaod::MatrixType/VectorType views (no copies), calls the C++ solver interface and
  * turns C++ exceptions into error codes, exactly where the reference's pyglue turns them into Python RuntimeErrors
  * (sqaodc/pyglue/pyglue.h:394-399). */
+#include <nvtx3/nvToolsExt.h>
 #include <sqaod_b200.h>
 #include <sqaod_b200/sqaod_api.hpp>
 #include "b200_solvers.hpp"
@@ -14,7 +15,13 @@ namespace sqc = sqaod::cuda;
 
 static thread_local std::string g_lastError;
 
-#define SQB_TRY try {
+/* every C-ABI call is an NVTX range named after the entry point (visible in Nsight Systems / Compute timelines; header-only
+ * NVTX3: a no-op unless a profiler injects itself) */
+struct SqbNvtxScope {
+    explicit SqbNvtxScope(const char *name) { nvtxRangePushA(name); }
+    ~SqbNvtxScope() { nvtxRangePop(); }
+};
+#define SQB_TRY SqbNvtxScope sqbNvtxScope_(__func__); try {
 #define SQB_CATCH                                                          \
     }                                                                      \
     catch (const std::exception &e) { g_lastError = e.what(); return 1; }  \
@@ -215,6 +222,7 @@ int sqb_dg_annealer_get_barrier_cycles(sqb_handle ann, unsigned long long *dot, 
 }
 int sqb_dg_annealer_get_counters(sqb_handle ann, unsigned long long *out8, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getCounters(out8)) SQB_CATCH }
 int sqb_dg_annealer_get_cta_profile(sqb_handle ann, unsigned long long *out, int max_ctas, int *n, int dtype) { SQB_TRY DISPATCH(dtype, *n = DGAX(real)->getCtaProfile(out, max_ctas)) SQB_CATCH }
+int sqb_dg_annealer_get_fields(sqb_handle ann, void *H, int ldH, int *valid, int dtype) { SQB_TRY DISPATCH(dtype, *valid = DGAX(real)->getFields((real *)H, ldH) ? 1 : 0) SQB_CATCH }
 int sqb_dg_annealer_get_profile(sqb_handle ann, unsigned long long *out16, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->getProfile(out16)) SQB_CATCH }
 int sqb_dg_annealer_set_sweep_mode(sqb_handle ann, int mode, int field_refresh, int dtype) { SQB_TRY DISPATCH(dtype, DGAX(real)->setSweepMode(mode, field_refresh)) SQB_CATCH }
 int sqb_dg_annealer_get_sweep_mode(sqb_handle ann, int *mode, int dtype) { SQB_TRY DISPATCH(dtype, *mode = DGAX(real)->fieldMode() ? 1 : 0) SQB_CATCH }

@@ -2138,6 +2138,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     dq_.alloc(dev_, (size_t)rows * ldq_);
     dE_.alloc(dev_, rows);
     E_.resize(rows);
+    eBack_.alloc(dev_, rows);
     hq_.assign((size_t)rows * ldq_, 0);
 
     /* launch geometry of the sweep */
@@ -2230,7 +2231,10 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
         /* the tcgen05 GEMM costs ~1 % of a step: refresh every step; the CUDA-core GEMM (fp64) only now and then */
         bool tc = false;
         if constexpr (std::is_same<real, float>::value) tc = tcJ_.ready && tcEnabled();
-        fieldRefresh_ = tc ? 1 : 16;
+        /* fields are carried from step to step (written back by the sweep) and recomputed from the spins every 8 steps on the tensor
+         * cores (16 on CUDA cores): after 25 steps without any recomputation they are within 5e-6 relative of a float64 evaluation
+         * (tests/test_dense_annealer_gpu.py::test_field_writeback_drift_is_bounded), i.e. within the rounding of one fp32 dot product */
+        fieldRefresh_ = tc ? 8 : 16;
         if (getenv("SQAOD_B200_FIELD_REFRESH")) fieldRefresh_ = std::max(1, atoi(getenv("SQAOD_B200_FIELD_REFRESH")));
         if (fieldRefreshWanted_ > 0) fieldRefresh_ = fieldRefreshWanted_;
     }
@@ -2331,6 +2335,7 @@ template <class real> const sq::BitSetArray &B200DenseGraphAnnealer<real>::get_q
 }
 template <class real> const sq::VectorType<real> &B200DenseGraphAnnealer<real>::get_E() const {
     if (!isEAvailable()) const_cast<This *>(this)->calculate_E();
+    const_cast<This *>(this)->eBack_.wait(const_cast<This *>(this)->E_.data, (size_t)m_ * nReplicas_);
     return E_;
 }
 
@@ -2352,8 +2357,7 @@ template <class real> void B200DenseGraphAnnealer<real>::calculate_E() {
         }
     }
     if (!done) devBatchedEnergy<real>(*dev_, dE_.p, dJ_.p, ldJ_, N_, N_, dq_.p, ldq_, dq_.p, ldq_, dh_.p, NULL, m_ * nReplicas_, -sign, -sign * c_);
-    dev_->d2h(E_.data, dE_.p, sizeof(real) * m_ * nReplicas_);
-    dev_->synchronize();
+    eBack_.enqueue(dE_.p, (size_t)m_ * nReplicas_); /* asynchronous: get_E() waits for this copy's own event, not for the stream */
     setState(solEAvailable);
 }
 
@@ -2369,6 +2373,7 @@ template <class real> real B200DenseGraphAnnealer<real>::getSystemE(real G, real
     sqb_throwErrorIf(nReplicas_ > 1, "getSystemE is defined per solver instance; not available on a replica batch.");
     sqb_throwErrorIf(ringWorld_ > 1, "getSystemE is not available on a shard of a trotter ring; gather the spins (multigpu.RingShardedDenseAnnealer.get_system_E).");
     self->calculate_E();
+    self->eBack_.wait(self->E_.data, (size_t)m_ * nReplicas_);
     real E = E_.sum() / m_;
     if (sq::isSQAAlgorithm(algo_)) {
         real spinDotSum = (real)ringSpinDot(*dev_, dq_.p, ldq_, N_, m_);
@@ -2474,6 +2479,23 @@ template <class real> void B200DenseGraphAnnealer<real>::setSweepMode(int mode, 
     sweepModeWanted_ = mode;
     fieldRefreshWanted_ = std::max(0, fieldRefresh);
     clearState(solPrepared);
+}
+
+/* extras: the local fields the field-mode sweep carries from step to step, as H[y][j] = h[j] + 2 sum_i J[j][i] q[y][i]
+ * (tests bound their drift against a fresh evaluation).  Returns false when no carried fields exist. */
+template <class real> bool B200DenseGraphAnnealer<real>::getFields(real *H, int ldH) const {
+    if (!fieldMode_ || !fieldsValid_ || !isPrepared()) return false;
+    const int rows = m_ * nReplicas_;
+    std::vector<real> F((size_t)rows * ldJ_), h(N_);
+    dev_->d2h(F.data(), dF_.p, sizeof(real) * F.size());
+    dev_->d2h(h.data(), dh_.p, sizeof(real) * N_);
+    dev_->synchronize();
+    for (int y = 0; y < rows; ++y)
+        for (int j = 0; j < N_; ++j) {
+            const real f = F[(size_t)y * ldJ_ + j];
+            H[(size_t)y * ldH + j] = fieldsHaveH_ ? f : h[j] + real(2) * f;
+        }
+    return true;
 }
 
 template <class real> void B200DenseGraphAnnealer<real>::refreshFields() {

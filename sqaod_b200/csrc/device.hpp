@@ -6,6 +6,7 @@
 #include <sqaod_b200/sqaod_api.hpp>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace sqb {
 
@@ -53,6 +54,46 @@ private:
 };
 
 B200Device &asB200(sq::cuda::Device &dev);
+
+/* Asynchronous device -> host read-back of a small result (the energies): the copy lands in pinned host memory and is fenced by its
+ * own event, so calculate_E() only ENQUEUES work and the launch stream is never synchronised; whoever reads the values (get_E)
+ * waits for that event alone.  (The reference synchronises the whole device per query, CUDADenseGraphAnnealer.cu:185-192, 337-351.) */
+template <class T> struct AsyncReadback {
+    AsyncReadback() : dev(NULL), host(NULL), n(0), ev(NULL), pending(false) {}
+    ~AsyncReadback() { release(); }
+    void alloc(const B200Device *d, size_t count) {
+        if (host && dev == d && n == count) { pending = false; return; } /* solvers re-prepare often: keep the pinned buffer */
+        release();
+        dev = d; n = count;
+        host = (T *)d->allocPinned(sizeof(T) * (count ? count : 1));
+        d->makeCurrent();
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    void release() {
+        if (host && dev) dev->freePinned(host);
+        if (ev) cudaEventDestroy(ev);
+        host = NULL; ev = NULL; n = 0; pending = false;
+    }
+    void enqueue(const T *devPtr, size_t count) { /* after the kernels that produce devPtr, on the device's stream */
+        dev->d2h(host, devPtr, sizeof(T) * count);
+        CUDA_CHECK(cudaEventRecord(ev, dev->stream()));
+        pending = true;
+    }
+    void wait(T *dst, size_t count) { /* no-op when nothing is in flight */
+        if (!pending) return;
+        CUDA_CHECK(cudaEventSynchronize(ev));
+        memcpy(dst, host, sizeof(T) * count);
+        pending = false;
+    }
+    const B200Device *dev;
+    T *host;
+    size_t n;
+    cudaEvent_t ev;
+    bool pending;
+private:
+    AsyncReadback(const AsyncReadback &);
+    AsyncReadback &operator=(const AsyncReadback &);
+};
 
 template <class T> struct DevBuf { /* RAII device array tied to a device */
     DevBuf() : dev(NULL), p(NULL), n(0) {}

@@ -231,6 +231,12 @@ class DenseGraphAnnealer(_SolverBase):
         _lib.check(L.sqb_dg_annealer_get_sweep_mode(self._cobj, C.byref(v), self._dt))
         return 'field' if v.value else 'classic'
 
+    def get_fields(self):
+        """field mode with carried fields: H[y][j] = h[j] + 2 sum_i J[j][i] q[y][i] as the sweep left it, or None"""
+        H = np.empty((self._m(), self.get_problem_size()), self.dtype); ok = C.c_int(0)
+        _lib.check(L.sqb_dg_annealer_get_fields(self._cobj, ptr(H), H.shape[1], C.byref(ok), self._dt))
+        return H if ok.value else None
+
     def get_cta_profile(self):
         """per-CTA profile of the last field-mode sweep: array (n_ctas, 8), see sqb_dg_annealer_get_cta_profile"""
         out = np.zeros((512, 16), np.uint64); n = C.c_int(0)

@@ -60,6 +60,37 @@ def main():
                 print('case N=%d m=%d %s: %s' % (N, m, np.dtype(dtype).name, 'ok' if (done and ok_all) else 'FAILED'), flush=True)
             if not done:
                 ok_all = False
+    # ---- the C5b row length: N = 32768 (J = 4 GiB per GPU, generated in place on every GPU), a few trotters per GPU, one step
+    # against the oracle (rank 0 runs it; the host copy of W comes from the same device generator)
+    N, m = 32768, 2 * world
+    gen = sq.dense_graph_annealer(None, sq.minimize, np.float32)
+    done = False
+    for seed in (1, 2, 3):
+        ring = RingShardedDenseAnnealer(('random', N, 32768, True), 0, np.float32, n_trotters=m)
+        ring.seed(seed); ring.prepare(); ring.randomize_spin()
+        ring.anneal_one_step(0.5, 20.0)
+        got = ring.gather_spins()
+        verdict = np.zeros(1, np.int64)
+        if rank == 0:
+            W = gen.get_qubo_random(N, 32768, True)
+            ref = orc.DenseGraphAnnealer(W, 0, np.float32, n_trotters=m, algorithm='coloring', n_workers=orc.num_threads(), rng='philox')
+            ref.seed(seed); ref.prepare(); ref.randomize_spin()
+            ref.anneal_one_step(0.5, 20.0)
+            same = np.array_equal(got, ref.get_q())
+            verdict[0] = 1 if same else (2 if ref.stats()[1] > 0 else 0)   # 1 equal, 2 borderline accept test: next seed, 0 mismatch
+            del W, ref
+        v = torch.from_numpy(verdict).cuda()
+        dist.broadcast(v, 0)
+        del ring
+        if int(v.item()) == 1:
+            done = True
+            break
+        if int(v.item()) == 0:
+            break
+    if rank == 0:
+        print('case N=%d m=%d float32 (C5b row length): %s' % (N, m, 'ok' if done else 'FAILED'), flush=True)
+    if not done:
+        ok_all = False
     dist.barrier()
     if rank == 0:
         print('RING_SHARD_OK' if ok_all else 'RING_SHARD_FAILED', flush=True)

@@ -17,26 +17,55 @@ def schedule(steps, Ginit=5.0, Gfin=0.01):
 
 
 def compare(e_gpu, e_ref, ground):
-    hit_g, hit_r = float((e_gpu == ground).mean()), float((e_ref == ground).mean())
+    # energies of the same configuration agree to 1e-5 relative between the solvers (north_star), exactly on dyadic inputs
+    tol = 2e-5 * max(1.0, abs(ground))
+    hit_g, hit_r = float((e_gpu <= ground + tol).mean()), float((e_ref <= ground + tol).mean())
     p = 0.5 * (hit_g + hit_r)
     sigma = max(np.sqrt(2 * p * (1 - p) / NSEEDS), 1e-3)
     assert abs(hit_g - hit_r) < 4 * sigma, 'ground-state hit rate %.3f (B200) vs %.3f (reference CPU)' % (hit_g, hit_r)
-    assert stats.ks_2samp(e_gpu, e_ref).pvalue > 1e-3
+    # the same configuration gets energies that differ in the last fp32 digits on the two solvers (non-dyadic W): merge levels
+    # closer than the energy tolerance before comparing the distributions
+    levels = []
+    for v in np.sort(np.concatenate([e_gpu, e_ref])):
+        if not levels or v - levels[-1] > tol:
+            levels.append(v)
+    levels = np.asarray(levels)
+    snap = lambda e: levels[np.searchsorted(levels, e + tol, side='right') - 1]
+    assert stats.ks_2samp(snap(e_gpu), snap(e_ref)).pvalue > 1e-3
     se = np.sqrt(e_gpu.var() / NSEEDS + e_ref.var() / NSEEDS) + 1e-9
-    assert abs(e_gpu.mean() - e_ref.mean()) < 4 * se
+    assert abs(e_gpu.mean() - e_ref.mean()) < 4 * se + tol
     return hit_g, hit_r
 
 
-@pytest.mark.parametrize('N,m,steps,algo', [(24, 4, 4, 'coloring'), (64, 16, 20, 'coloring'), (48, 8, 12, 'sa_naive')])
-def test_dense_final_energy_distribution(oracle, N, m, steps, algo):
+def nondyadic_symmetric_W(N, seed):
+    """U(-0.5, 0.5) symmetric, NOT rounded to a grid: sums are inexact in fp32, so the field-mode sweep's incrementally updated
+    local fields and the split-bf16 GEMM that seeds them differ from a fresh fp32 evaluation by rounding"""
+    rng = np.random.default_rng(seed)
+    A = rng.random((N, N)) - 0.5
+    return np.asarray(np.triu(A) + np.triu(A, 1).T, np.float32)
+
+
+# (N, m, steps, algorithm, sweep mode, field_refresh, W): the first three run in the automatic mode (classic kernel at these
+# shapes); the 'field' rows force the HEADLINE kernel -- 3-4 trotters per CTA as at C2 (512 trotters on 148 SMs), non-dyadic W,
+# fields recomputed every step and carried over 8 steps
+STAT_CASES = [(24, 4, 4, 'coloring', 'auto', 0, 'dyadic'), (64, 16, 20, 'coloring', 'auto', 0, 'dyadic'), (48, 8, 12, 'sa_naive', 'auto', 0, 'dyadic'),
+              (48, 512, 12, 'coloring', 'field', 1, 'real'), (40, 512, 16, 'coloring', 'field', 8, 'real'), (40, 512, 10, 'sa_naive', 'field', 8, 'real')]
+
+
+@pytest.mark.parametrize('N,m,steps,algo,mode,refresh,wkind', STAT_CASES)
+def test_dense_final_energy_distribution(oracle, N, m, steps, algo, mode, refresh, wkind):
     import sqaod_b200 as sq
-    W = quantized_symmetric_W(N, 2024, np.float32)
+    W = quantized_symmetric_W(N, 2024, np.float32) if wkind == 'dyadic' else nondyadic_symmetric_W(N, 2024)
     beta = 1. / 0.02
     Gs = schedule(steps) if algo == 'coloring' else schedule(steps, 2.0, 0.02)
     ann = sq.dense_graph_annealer(W, sq.minimize, np.float32, n_trotters=m, algorithm=algo)
+    if mode != 'auto':
+        ann.set_sweep_mode(mode, refresh)
     e_gpu, e_ref = np.empty(NSEEDS), np.empty(NSEEDS)
     for s in range(NSEEDS):
         ann.seed(s); ann.prepare(); ann.randomize_spin()
+        if s == 0 and mode != 'auto':
+            assert ann.get_sweep_mode() == mode
         for G in Gs:
             ann.anneal_one_step(G, beta)
         e_gpu[s] = ann.get_E().min()

@@ -67,27 +67,35 @@ CASES = [(5, 4, 6, 'coloring', 4), (40, 24, 7, 'coloring', 3), (100, 130, 32, 'c
 @pytest.mark.parametrize('dtype', DT)
 @pytest.mark.parametrize('N0,N1,m,algo,steps', CASES)
 def test_exact_chain_vs_oracle(sq, oracle, N0, N1, m, algo, steps, dtype):
-    """same Philox stream -> identical spins after every step (quantised inputs keep the contraction exact)."""
+    """same Philox stream -> identical spins after every step (quantised inputs keep the contraction exact).  No mismatch is
+    forgiven: the oracle counts the accept tests that sat within a rounding error of their threshold, and only a seed that hit
+    one may part from the kernel -- it is then replaced by the next seed (the dense tests' rule)."""
     b0, b1, W = quantized_bipartite(N0, N1, 500 + N0, dtype)
-    seed = 9
-    ref = oracle.BipartiteGraphAnnealer(b0, b1, W, 0, dtype, n_trotters=m, algorithm=algo, rng='philox')
-    ref.seed(seed); ref.prepare(); ref.randomize_spin()
-    ann = sq.bipartite_graph_annealer(b0, b1, W, sq.minimize, dtype, n_trotters=m, algorithm=algo)
-    ann.seed(seed); ann.prepare(); ann.randomize_spin()
-    G, beta = (3.0, 1. / 0.3) if algo == 'coloring' else (2.0, 1.0)
-    for s in range(steps + 1):
-        q = ann.get_q()
-        got0, got1 = np.stack([p[0] for p in q]), np.stack([p[1] for p in q])
-        want0, want1 = ref.get_q()
-        nbad = int((got0 != want0).sum() + (got1 != want1).sum())
-        # an accept test can sit on a rounding edge (exp, fma contraction); allow a handful of such spins per step
-        assert nbad <= (0 if s == 0 else 2 * s), 'step %d: %d spins differ' % (s, nbad)
-        if nbad:
-            ann.set_qset(list(zip(want0, want1)))      # re-synchronise and keep checking the following steps
-        if s < steps:
-            ref.anneal_one_step(G, beta); ann.anneal_one_step(G, beta)
-            G *= 0.7
-    assert np.allclose(ann.get_E(), ref.get_E(), rtol=tol(dtype), atol=tol(dtype) * 10)
+    for seed in range(9, 29):
+        ref = oracle.BipartiteGraphAnnealer(b0, b1, W, 0, dtype, n_trotters=m, algorithm=algo, rng='philox')
+        ref.seed(seed); ref.prepare(); ref.randomize_spin()
+        ann = sq.bipartite_graph_annealer(b0, b1, W, sq.minimize, dtype, n_trotters=m, algorithm=algo)
+        ann.seed(seed); ann.prepare(); ann.randomize_spin()
+        G, beta = (3.0, 1. / 0.3) if algo == 'coloring' else (2.0, 1.0)
+        same = True
+        for s in range(steps + 1):
+            q = ann.get_q()
+            got0, got1 = np.stack([p[0] for p in q]), np.stack([p[1] for p in q])
+            want0, want1 = ref.get_q()
+            nbad = int((got0 != want0).sum() + (got1 != want1).sum())
+            if nbad:
+                assert s > 0, 'randomize_spin stream differs'
+                assert ref.stats()[1] > 0, 'seed %d step %d: %d spins differ without a borderline accept test' % (seed, s, nbad)
+                same = False
+                break
+            if s < steps:
+                ref.anneal_one_step(G, beta); ann.anneal_one_step(G, beta)
+                G *= 0.7
+        if same:
+            assert ref.stats()[0] > 0
+            assert np.allclose(ann.get_E(), ref.get_E(), rtol=tol(dtype), atol=tol(dtype) * 10)
+            return
+    pytest.fail('no seed without a borderline accept test')
 
 
 @pytest.mark.parametrize('dtype', DT)

@@ -299,3 +299,61 @@ def test_automatic_sweep_mode(sq):
     c.set_sweep_mode('field')
     with pytest.raises(RuntimeError, match='shared memory'):
         c.prepare()
+
+
+@pytest.mark.parametrize('N,m', [(1000, 296), (8192, 512)])
+def test_field_writeback_drift_is_bounded(sq, N, m):
+    """Field mode with carried fields on NON-dyadic J: after many steps the fields the sweep wrote back (seeded by the split-bf16
+    tensor-core GEMM, then updated in fp32 with one J row per accepted flip) stay within a few fp32 roundings of a fresh float64
+    evaluation h + 2 J q of the spins they belong to -- 50 steps without any recomputation (the production default refreshes far
+    more often)."""
+    rng = np.random.default_rng(N)
+    A = rng.random((N, N), dtype=np.float32) - np.float32(0.5)
+    W = np.ascontiguousarray(np.triu(A) + np.triu(A, 1).T)
+    ann = sq.dense_graph_annealer(W, sq.minimize, np.float32, n_trotters=m)
+    ann.set_sweep_mode('field', 1000)
+    ann.seed(3); ann.prepare(); ann.randomize_spin()
+    assert ann.get_fields() is None                      # nothing carried yet
+    G, nsteps = 2.0, (50 if N < 4096 else 25)
+    for _ in range(nsteps):
+        ann.anneal_one_step(G, 50.0)
+        G *= 0.85
+    H = ann.get_fields()
+    assert H is not None
+    h, J, c = ann.get_hamiltonian()
+    q = ann.get_spins().astype(np.float64)
+    rows = np.arange(0, m, max(1, m // 16))
+    fresh = h.astype(np.float64)[None, :] + 2.0 * (q[rows] @ J.astype(np.float64).T)
+    err = np.abs(H[rows].astype(np.float64) - fresh).max()
+    scale = np.abs(fresh).max()
+    flips = ann.get_stats()['accepted'] / float(m)
+    print('N=%d m=%d: %d steps, %.0f accepted flips per trotter, max |H - fresh| = %.3g (fields up to %.3g)' % (N, m, nsteps, flips, err, scale))
+    assert flips > 100
+    assert err <= 2e-4 * max(1.0, scale)
+
+
+def test_problem_batch_then_single_problem(sq):
+    """a problem batch followed by set_hamiltonian / set_qubo on the same solver anneals ONE problem again (the batch state is reset)"""
+    N, m, R = 48, 6, 3
+    Ws = np.stack([quantized_symmetric_W(N, 70 + r, np.float32) for r in range(R)])
+    ann = sq.dense_graph_annealer(None, sq.minimize, np.float32)
+    ann.set_qubo_batch(Ws)
+    ann.set_preferences(n_trotters=m)
+    ann.seed(1); ann.prepare(); ann.randomize_spin()
+    ann.anneal_one_step(1.0, 10.0)
+    assert ann.get_E().shape[0] == R * m
+    one = sq.dense_graph_annealer(Ws[1], sq.minimize, np.float32, n_trotters=m)
+    h, J, c = one.get_hamiltonian()
+    for setter in ('hamiltonian', 'qubo'):
+        if setter == 'hamiltonian':
+            ann.set_hamiltonian(h, J, c)
+        else:
+            ann.set_qubo(Ws[1])
+        ann.set_preferences(n_trotters=m)
+        ann.seed(9); ann.prepare(); ann.randomize_spin()
+        one.seed(9); one.prepare(); one.randomize_spin()
+        for G in (2.0, 0.5):
+            ann.anneal_one_step(G, 10.0); one.anneal_one_step(G, 10.0)
+        assert ann.get_E().shape[0] == m
+        assert np.array_equal(ann.get_spins(), one.get_spins())
+        assert np.allclose(ann.get_E(), one.get_E(), rtol=1e-5, atol=1e-4)

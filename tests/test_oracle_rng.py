@@ -50,3 +50,32 @@ def test_mt_against_reference_object_code(oracle):
         f, d = oracle.mt_reals(seed, n)
         assert np.array_equal(f, wf) and np.array_equal(d, wd)
         assert f.min() >= 0 and d.min() >= 0 and d.max() < 1
+
+
+def test_dot_product_against_reference_object_code(oracle):
+    """the oracle's AVX2 dot product (oracle.cpp dotv: 'same summation tree') vs the reference's own cpu/Dot_SIMD.cpp, compiled where it
+    lies into oracle/_ref: bit-identical on 64-byte aligned, zero-padded rows of every length class (the reference reads whole
+    cache lines, Matrix.cpp:7-14 clears the padding)"""
+    ref = oracle.reflib()
+    if ref is None:
+        pytest.skip('oracle/_ref not built (reference tree absent)')
+    import ctypes as C
+    lib = oracle.lib()
+    lib.orc_dot_f32.restype = C.c_float; lib.orc_dot_f64.restype = C.c_double
+    ref.ref_dot_f32.restype = C.c_float; ref.ref_dot_f64.restype = C.c_double
+    rng = np.random.default_rng(5)
+
+    def aligned(n, dtype):
+        per = 64 // np.dtype(dtype).itemsize
+        cap = (n + per - 1) // per * per + per
+        raw = np.zeros(cap * np.dtype(dtype).itemsize + 64, np.uint8)
+        off = (-raw.ctypes.data) % 64
+        a = raw[off:off + cap * np.dtype(dtype).itemsize].view(dtype)
+        a[:n] = rng.standard_normal(n).astype(dtype)
+        return a, raw
+    for n in (1, 7, 8, 15, 16, 17, 100, 1000, 1024, 4097, 8192):
+        for dtype, fo, fr in ((np.float32, lib.orc_dot_f32, ref.ref_dot_f32), (np.float64, lib.orc_dot_f64, ref.ref_dot_f64)):
+            a, ka = aligned(n, dtype); b, kb = aligned(n, dtype)
+            pa, pb = a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)
+            got, want = fo(pa, pb, n), fr(pa, pb, n)
+            assert got == want, (n, dtype, got, want)

@@ -51,16 +51,20 @@ def main():
     ap.add_argument('--skip-bipartite', action='store_true')
     args = ap.parse_args()
     import sqaod_b200 as sq
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
     dtype = np.dtype(args.dtype).type
     rng = np.random.default_rng(7)
     dense, bip = [], []
     for N in [int(v) for v in args.sizes.split(',')]:
         W = sq.generate_random_symmetric_W(N, dtype=dtype)
+        # the sweep kernels carry at most 32 trotters per CTA: m <= 32 x #SMs (4736 on a B200); beyond that the size runs with that m
+        m = min(N, 32 * sms)
         ann = sq.dense_graph_annealer(W, sq.minimize, dtype)
-        ann.set_preferences(n_trotters=N)
+        ann.set_preferences(n_trotters=m)
         n_it, sec = anneal(ann, args.duration)
-        out = {'solver': 'dense', 'N': N, 'm': N, 'dtype': args.dtype, 'sweep_mode': ann.get_sweep_mode(), 'n_iters': n_it,
-               'ms_per_step': sec * 1e3, 'attempts_per_s': N * N / sec}
+        out = {'solver': 'dense', 'N': N, 'm': m, 'dtype': args.dtype, 'sweep_mode': ann.get_sweep_mode(), 'n_iters': n_it,
+               'ms_per_step': sec * 1e3, 'attempts_per_s': N * m / sec}
         dense.append((N, n_it, sec))
         del ann
         if not args.skip_bipartite:

@@ -2148,6 +2148,14 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     if (nReplicas_ > 1) {
         const int gMin = (m_ + 31) / 32;
         G = std::max(gMin, std::min(G, dev_->numSMs() / std::min(nReplicas_, dev_->numSMs())));
+        /* field mode wants at most four trotters per CTA (one accept-chain warp each): when the field rows fit in that geometry,
+         * a replica gets ceil(m / 4) CTAs and fewer replicas share a launch */
+        const char *feR = getenv("SQAOD_B200_SWEEP_FIELD");
+        const bool fieldAllowed = ringWorld_ <= 1 && nProblems_ <= 1 && sweepModeWanted_ != 0 && !(feR && atoi(feR) == 0);
+        const int Gf = std::max(gMin, std::min(dev_->numSMs(), (int)(m_ + 3) / 4));
+        if (fieldAllowed && Gf > G &&
+            SweepSmem<real>((m_ + Gf - 1) / Gf, packedWords64(N_), 128, 0, SW_MAX_K, SW_FIELD_WARPS, sq::roundUp(N_, 128)).total <= dev_->smemPerBlockOptin())
+            G = Gf;
     }
     replicasPerLaunch_ = std::max(1, std::min(nReplicas_, dev_->numSMs() / G));
     const int maxT = (m_ + G - 1) / G;
@@ -2178,15 +2186,14 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
             }
         }
         /* Field mode: no TMA ring, T rows of local fields instead (traffic: acceptance rate x one J row per attempt instead of
-         * one row per attempt).  Automatic choice, from the size sweep in benchmarks/README.md: when the rows fit next to the
-         * tables AND either J is too large for L2 (the classic kernel is then HBM-bound: C2 3.9 vs 14 ms) or a CTA carries 3-4
-         * trotters (N = m = 512: 0.32 vs 0.39 ms); with 1-2 trotters per CTA the classic kernel's look-ahead dot products already
-         * hide behind the chain, and with many trotters per CTA the field warps' per-window work (cross-term gathers, T K of
-         * them) outweighs the saved rows (N = m = 1024 / 2048: 1.1 / 5.2 vs 0.9 / 4.1 ms).  set_sweep_mode() or
-         * SQAOD_B200_SWEEP_FIELD=0/1 override.  Not combined with ring sharding or problem batches. */
+         * one row per attempt).  Automatic choice: whenever the rows fit next to the tables -- with this round's chain (one warp per
+         * trotter, cross terms per accepted flip, table pre-pass) it wins at every size of the reference's N list where it fits
+         * (m = N, ms per step classic / field: N = 128 0.099 / 0.065, 512 0.37 / 0.13, 1024 0.83 / 0.32, 2048 4.2 / 0.87; from
+         * N = m = 3072 on the rows of the 21+ trotters per CTA do not fit).  set_sweep_mode() or SQAOD_B200_SWEEP_FIELD=0/1
+         * override.  Not combined with ring sharding or problem batches. */
         fieldMode_ = false;
         const char *fe = getenv("SQAOD_B200_SWEEP_FIELD");
-        const bool fieldAuto = ((size_t)N_ * ldJ_ * sizeof(real) > ((size_t)64 << 20)) || (maxT >= 3 && maxT <= 4);
+        const bool fieldAuto = true;
         const bool fieldWanted = (sweepModeWanted_ >= 0) ? sweepModeWanted_ != 0 : (fe ? atoi(fe) != 0 : fieldAuto);
         sqb_throwErrorIf(sweepModeWanted_ == 1 && (ringWorld_ > 1 || nProblems_ > 1), "field mode cannot be combined with ring sharding or problem batches.");
         if (fieldWanted && ringWorld_ <= 1 && nProblems_ <= 1) {

@@ -283,13 +283,21 @@ def test_field_mode_equals_classic_mode(sq, N, m, algo, steps, G0, dtype):
 
 
 def test_automatic_sweep_mode(sq):
-    # 3-4 trotters per CTA (or J beyond L2): field mode; 1-2 trotters per CTA: the classic kernel (prepare()'s measured rule)
+    # field mode whenever the field rows fit in shared memory (prepare()'s measured rule) ...
     a = sq.dense_graph_annealer(quantized_symmetric_W(192, 5), sq.minimize, np.float32, n_trotters=512)
     a.prepare()
     assert a.get_sweep_mode() == 'field'
     a = sq.dense_graph_annealer(quantized_symmetric_W(256, 5), sq.minimize, np.float32, n_trotters=64)
     a.prepare()
+    assert a.get_sweep_mode() == 'field'
+    a.set_sweep_mode('classic')
+    a.prepare()
     assert a.get_sweep_mode() == 'classic'
+    # ... and with a replica batch, in a geometry of at most four trotters per CTA
+    r = sq.dense_graph_annealer(quantized_symmetric_W(256, 5), sq.minimize, np.float32, n_trotters=64)
+    r.set_replicas(20)
+    r.prepare()
+    assert r.get_sweep_mode() == 'field'
     # 28 trotters per CTA x 2048 doubles do not fit: automatic mode falls back to the classic kernel, forcing field mode is an error
     W = quantized_symmetric_W(2048, 6, np.float64)
     b = sq.dense_graph_annealer(W, sq.minimize, np.float64, n_trotters=4000)

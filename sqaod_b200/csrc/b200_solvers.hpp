@@ -100,7 +100,7 @@ private:
 
     B200Device *dev_;
     DevBuf<real> dJ_, dh_, dE_;
-    DevBuf<signed char> dq_;
+    DevBuf<signed char> dq_, dq2_;  /* current spins; the buffer the next sweep writes (swapped after every step) */
     DevBuf<unsigned long long> dStats_;
     void *handoff_;            /* accept flags, snapshots, halo rows (HandoffLayout in dense_annealer.cu) */
     bool handoffIpc_;

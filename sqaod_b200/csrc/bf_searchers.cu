@@ -292,11 +292,15 @@ private:
         dev_->d2h(&count, dCount_.p, sizeof(count));
         dev_->synchronize();
         const unsigned long long spanSize = 1ull << (L_ + M_);
-        if (count > BF_COLLECT_CAP && (e - b) > spanSize) {
-            /* more ties than the gather buffer holds: halve the range on a span boundary, lower half first */
-            unsigned long long midSpan = ((b >> (L_ + M_)) + ((e - 1) >> (L_ + M_)) + 1) / 2;
-            unsigned long long mid = midSpan << (L_ + M_);
-            if (mid <= b || mid >= e) mid = b + (e - b) / 2;
+        if (count > BF_COLLECT_CAP && (e - b) > 1) {
+            /* more ties than the gather buffer holds: halve the range, lower half first -- on a span boundary while the range covers
+             * several spans, inside the span otherwise (the kernel takes arbitrary [rBegin, rEnd)), so that every leaf gathers ALL its
+             * ties and the ascending, capped list is the lowest `want` states whatever the degeneracy (W = 0 included) */
+            unsigned long long mid = b + (e - b) / 2;
+            if ((e - b) > spanSize) {
+                const unsigned long long midSpan = ((b >> (L_ + M_)) + ((e - 1) >> (L_ + M_)) + 1) / 2;
+                if ((midSpan << (L_ + M_)) > b && (midSpan << (L_ + M_)) < e) mid = midSpan << (L_ + M_);
+            }
             collectRec(fullBegin, fullEnd, b, mid, target, want, found);
             collectRec(fullBegin, fullEnd, mid, e, target, want, found);
             return;

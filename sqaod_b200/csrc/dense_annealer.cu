@@ -72,7 +72,9 @@ enum { SW_MAX_K = 16, SW_DOT_WARPS = 12 /* chain-critical layout */, SW_DOT_WARP
 template <class real> struct SweepParams {
     const real *J;
     const real *h;
-    signed char *q;
+    signed char *q;     /* spins at step start (read) */
+    signed char *qOut;  /* spins at step end (written): a second buffer, swapped by the host after the launch -- a CTA may still be
+                         * packing a neighbour's step-start row while the owner of that row has finished the sweep */
     int ldJ, ldq, N, m;
     unsigned long long seed, step;
     real twoDivM, coef, beta;
@@ -708,15 +710,17 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
      * Rows of window w are reduced against S_{w-1} (S_0 for w = 0), i.e. they can start as soon as window w-2 has been
      * replayed, one full window before the chain needs them. */
     const uint32_t aSync = smemAddr(taskCounter);
-    const uint32_t aRowsDone = aSync + 4, aReplayDone = aSync + 12, aSnapCount = aSync + 16, aNbCount = aSync + 20, aPrepCount = aSync + 24;
+    /* rowsDone[2], nbCount, prepCount share one aligned 16-byte line: the accept chain polls all of them with ONE 128-bit load */
+    const uint32_t aRowsDone = aSync + 16, aReplayDone = aSync + 4, aSnapCount = aSync + 8, aNbCount = aSync + 24, aPrepCount = aSync + 28;
     auto waitCount = [&](uint32_t addr, uint32_t want, unsigned ns) { /* whole warp; lane 0 polls.  ns == 0: latency-critical (accept chain) */
-        if (lane == 0 && ldAcquireCta(addr) < want) {
+        const bool chainPoll = (ns == 0u); /* fence-free polls on the accept chain, see ldVolatileCta */
+        if (lane == 0 && (chainPoll ? ldVolatileCta(addr) : ldAcquireCta(addr)) < want) {
             const long long t0 = clock64();
             /* a waiting warp must not eat the issue slots of the warps it waits for (they share its scheduler): sleep between
              * polls, 32..128 ns for the chain, ns..8 ns for everybody else */
             const unsigned nsMax = ns ? ns * 8u : 128u;
             if (!ns) ns = 32u;
-            while (ldAcquireCta(addr) < want) {
+            while ((chainPoll ? ldVolatileCta(addr) : ldAcquireCta(addr)) < want) {
                 __nanosleep(ns);
                 if (ns < nsMax) ns <<= 1;
             }
@@ -856,7 +860,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     const uint32_t aFlipQ = smemAddr(flipQ);
     const uint32_t qMask = (uint32_t)L.flipQLen - 1u;
     auto pushFlip = [&](uint32_t payload) { /* one lane */
-        const uint32_t slot = atomicAdd(reinterpret_cast<unsigned int *>(taskCounter) + 7, 1u);
+        const uint32_t slot = atomicAdd(reinterpret_cast<unsigned int *>(taskCounter) + 3, 1u);
         const unsigned long long e = ((unsigned long long)(slot + 1u) << 32) | payload;
         asm volatile("st.relaxed.cta.shared.u64 [%0], %1;" ::"r"(aFlipQ + ((slot & qMask) << 3)), "l"(e) : "memory");
     };
@@ -903,7 +907,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
     if (tid == 0) {
         stReleaseCta(aRowsDone, 0u); stReleaseCta(aRowsDone + 4, 0u); stReleaseCta(aReplayDone, 0u);
         stReleaseCta(aSnapCount, 1u); stReleaseCta(aNbCount, 1u); stReleaseCta(aPrepCount, FIELD ? 4u : 3u);
-        stReleaseCta(aSync + 28, 0u); /* tail of the flip queue (field mode) */
+        stReleaseCta(aSync + 12, 0u); /* tail of the flip queue (field mode) */
     }
     __syncthreads();
     const long long tLoop0 = clock64();
@@ -1113,13 +1117,30 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             const int Kw = roundsIn(w), KwN = (w + 1 < nW) ? roundsIn(w + 1) : 0;
             const int buf = w & 1, slot = w & (TAB - 1), slotN = (w + 1) & (TAB - 1);
             const uint32_t wBase = (uint32_t)(w * K);
-            const long long wt0 = waited;
-            waitCount(aRowsDone + 4u * (uint32_t)buf, (uint32_t)(P.dotWarps * ((w >> 1) + 1)), 0);
-            const long long wt1 = waited;
-            if (remote) waitCount(aNbCount, (uint32_t)w + 1u, 0);
-            const long long wt2 = waited;
-            waitCount(aPrepCount, (uint32_t)min(w + 2, nW), 0); /* the gathers of a commit look at the next window's draws */
-            waitedRows += wt1 - wt0; waitedNbF += wt2 - wt1;
+            {   /* what the window needs: its local fields (field warps), the foreign neighbours' snapshot, the tables of windows w and
+                 * w+1 (the gathers of a commit look one window ahead) -- one 128-bit poll of the four counters */
+                const uint32_t wantRows = (uint32_t)(P.dotWarps * ((w >> 1) + 1)), wantNb = remote ? (uint32_t)w + 1u : 0u, wantPrep = (uint32_t)min(w + 2, nW);
+                if (lane == 0) {
+                    uint32_t c0, c1, c2, c3;
+                    unsigned ns = 32u;
+                    long long tFirst = 0, tRows = 0;
+                    for (;;) {
+                        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3) : "r"(aRowsDone) : "memory");
+                        const bool okRows = (buf ? c1 : c0) >= wantRows;
+                        if (okRows && tFirst && !tRows) tRows = clock64();
+                        if (okRows && c2 >= wantNb && c3 >= wantPrep) break;
+                        if (!tFirst) tFirst = clock64();
+                        __nanosleep(ns);
+                        if (ns < 128u) ns <<= 1;
+                    }
+                    if (tFirst) { /* split the wait: until the fields were there / the rest (neighbour data, tables) */
+                        const long long tEnd = clock64();
+                        if (!tRows) tRows = tEnd;
+                        waited += tEnd - tFirst; waitedRows += tRows - tFirst; waitedNbF += tEnd - tRows;
+                    }
+                }
+                __syncwarp();
+            }
             const unsigned long long flagBase = (P.roundBase + (unsigned long long)w * K + 1ull) << 1;
             const long long rrBase = (long long)w * K - K; /* round index of bit 0 of a remote conflict mask */
             const int fs0 = (w * K) % SW_FLAG_RING;
@@ -1234,7 +1255,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                             const uint32_t aP = aPend + (uint32_t)((t * 32 + lane) * sizeof(real));
                             if (want) cpAsyncReal(aP, Jrow + xGather); else stsReal(aP, real(0));
                             cpAsyncCommit();
-                            for (int i = lane; i < rowLines; i += 32) prefetchL2(Jrow + (size_t)i * (128 / sizeof(real)));
+                            if (lane == 1) prefetchL2Bulk(Jrow, (uint32_t)((size_t)P.ldJ * sizeof(real))); /* the whole row, for the field warps */
                             pwF = (uint32_t)w + 1u; pr0F = (uint32_t)rs;
                             pSF = upj ? corrScale : -corrScale;
                             accC |= 1u << rs; sgnC |= upj << rs;
@@ -1394,7 +1415,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
                         const uint32_t aP = aPend + (uint32_t)((t * 32 + lane) * sizeof(real));
                         if (xt >= 0) cpAsyncReal(aP, Jrow + xt); else stsReal(aP, real(0));
                         cpAsyncCommit();
-                        for (int i = lane; i < rowLines; i += 32) prefetchL2(Jrow + (size_t)i * (128 / sizeof(real)));
+                        if (lane == 1) prefetchL2Bulk(Jrow, (uint32_t)((size_t)P.ldJ * sizeof(real)));
                         if (lane == 0) {
                             cs[0] = (uint32_t)w + 1u; cs[1] = (uint32_t)rs;
                             cs[2] |= 1u << rs; cs[3] |= upj << rs;
@@ -1813,7 +1834,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) denseSweepKernel(const SweepPar
             int w64, bit;
             spinBitPos(j, w64, bit);
             unsigned nib = (unsigned)(qcur[(size_t)r * NW + w64] >> bit) & 0xfu;
-            signed char *dst = qBase + (size_t)(y0 + r) * P.ldq + j;
+            signed char *dst = P.qOut + (size_t)replica * P.qReplicaStride + (size_t)(y0 + r) * P.ldq + j;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (j + e < N) dst[e] = ((nib >> e) & 1u) ? 1 : -1;
@@ -2136,6 +2157,7 @@ template <class real> void B200DenseGraphAnnealer<real>::prepare() {
     const int rows = m_ * nReplicas_;
     ldq_ = sq::roundUp(N_, 16);
     dq_.alloc(dev_, (size_t)rows * ldq_);
+    dq2_.alloc(dev_, (size_t)rows * ldq_);
     dE_.alloc(dev_, rows);
     E_.resize(rows);
     eBack_.alloc(dev_, rows);
@@ -2395,7 +2417,7 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
     throwErrorIfQNotSet();
     clearState(solSolutionAvailable);
     SweepParams<real> P;
-    P.J = dJ_.p; P.h = dh_.p; P.q = dq_.p;
+    P.J = dJ_.p; P.h = dh_.p; P.q = dq_.p; P.qOut = dq2_.p;
     P.ldJ = ldJ_; P.ldq = ldq_; P.N = N_; P.m = m_;
     P.seed = seed_; P.step = step_;
     const bool sqa = (algo_ == sq::algoColoring);
@@ -2474,6 +2496,7 @@ template <class real> void B200DenseGraphAnnealer<real>::annealOneStep(real G, r
         CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid_, nr), dim3(SW_THREADS), args, smemBytes_, dev_->stream()));
         ++dev_->launchCount;
     }
+    std::swap(dq_.p, dq2_.p); /* the sweep wrote the new spins into the second buffer */
     ++launchCount_;
     ++step_;
     if (ringWorld_ > 1) ringPushHalos(); /* per-sweep boundary exchange over NVLink */

@@ -83,6 +83,15 @@ __device__ __forceinline__ uint32_t ldAcquireCta(uint32_t a) {
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
+/* plain (fence-free) poll of a shared-memory counter.  ld.acquire costs a fence, and a fence waits for everything the warp has
+ * in flight -- on the accept chain that includes the asynchronous cross-term gathers of the last commit (HBM latency).  The
+ * counters and the data they guard live in the shared memory of ONE SM, whose load/store unit executes a warp's accesses in
+ * program order, and the producers publish with st.release / red.release, so the data read after a successful poll is current. */
+__device__ __forceinline__ uint32_t ldVolatileCta(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ void stReleaseCta(uint32_t a, uint32_t v) { asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void redAddReleaseCta(uint32_t a, uint32_t v) {
     asm volatile("red.release.cta.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -96,6 +105,10 @@ __device__ __forceinline__ void cpAsyncReal(uint32_t dst, const double *src) {
 }
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+/* one instruction asks L2 for a whole contiguous block (TMA bulk prefetch, async proxy): addr 16-byte aligned, bytes a multiple of 16 */
+__device__ __forceinline__ void prefetchL2Bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 /* named barrier over `count` threads (a multiple of 32) of the CTA; warps may arrive from different code paths */
 __device__ __forceinline__ void namedBarSync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }

@@ -137,3 +137,21 @@ def test_bipartite_bf_vs_oracle(sq, oracle, N0, N1, dtype):
     s = sq.bipartite_graph_bf_searcher(np.ones(N0), np.ones(N1), np.ones((N1, N0)), sq.maximize, dtype)
     s.search()
     assert s.get_E()[0] == N0 * N1 + N0 + N1
+
+
+@pytest.mark.parametrize('dtype', DT)
+def test_massively_degenerate_problem_returns_the_lowest_states(sq, dtype):
+    """W = 0: every one of the 2^N states is an argmin -- far more ties than the gather buffer holds even inside one kernel span.
+    The solution list must be the `cap` LOWEST packed states in ascending order (CPU searcher semantics,
+    CPUDenseGraphBFSearcher.cpp:103-131), deterministically."""
+    N = 24
+    W = np.zeros((N, N), dtype)
+    s = sq.dense_graph_bf_searcher(W, sq.minimize, dtype)
+    s.search()
+    assert float(s.get_E()[0]) == 0.0
+    xs = s.get_packed_x()
+    assert len(xs) == 65536
+    assert np.array_equal(xs, np.arange(65536, dtype=np.uint64))
+    s2 = sq.dense_graph_bf_searcher(W, sq.minimize, dtype, tile_size=1 << 12)     # the cap follows the tile size
+    s2.search()
+    assert np.array_equal(s2.get_packed_x(), np.arange(1 << 12, dtype=np.uint64))

@@ -6,11 +6,16 @@
                                                          sqaodpy/sqaod/cuda/src/cuda_*.cpp), compiled unmodified against
                                                          include/sqaodc/sqaodc.h and linked to libsqaod_b200.so
     python tests/refsuite_runner.py cext [pytest args]   sqaod_b200.cext (the ctypes restatement of the same method tables)
+    python tests/refsuite_runner.py cpu  [pytest args]   no GPU: the reference's CPU back end itself (`make -C oracle refcpu`: sqaodc/common +
+                                                         sqaodc/cpu + the cpu_*.cpp glue, compiled unmodified against oracle/eigen_standin) under
+                                                         the reference's own CPU and pure-Python test classes -- checks that build, which the
+                                                         oracle is pinned against (tests/test_oracle_vs_reference_cpu.py)
 
 The reference's top-level sqaod/__init__.py imports the CPU extension (needs Eigen: not buildable here), so the package
 object is assembled here instead: sqaod.common, sqaod.py and sqaod.cuda (device.py, the four solver wrappers, formulas.py)
-are the reference's files; only the six C-extension modules underneath sqaod.cuda are ours.  sqaod.cpu is a stub, and the
-CPU test classes are deselected (-k cuda)."""
+are the reference's files; only the six C-extension modules underneath sqaod.cuda are ours.  In the glue / cext runs sqaod.cpu is a stub
+and the CPU test classes are deselected (-k cuda); in the cpu run sqaod.cpu is the reference's package over oracle/_ref/refsuite/glue_cpu
+and sqaod.cuda is absent (is_cuda_available() is False, so the reference's tests define no CUDA classes)."""
 import importlib
 import importlib.util
 import os
@@ -19,6 +24,7 @@ import types
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SUITE = os.path.join(ROOT, 'oracle', '_ref', 'refsuite')
+CPU_CEXT = ['cpu_dg_annealer', 'cpu_bg_annealer', 'cpu_dg_bf_searcher', 'cpu_bg_bf_searcher', 'cpu_formulas']
 CEXT = ['cuda_device', 'cuda_dg_annealer', 'cuda_bg_annealer', 'cuda_dg_bf_searcher', 'cuda_bg_bf_searcher', 'cuda_formulas']
 
 
@@ -41,8 +47,11 @@ def assemble(binding):
         if not k.startswith('_'):
             setattr(pkg, k, getattr(c, k))
     pkg.common = c
-    pkg.is_cuda_available = lambda: True
+    pkg.is_cuda_available = lambda: binding != 'cpu'
     pkg.py = importlib.import_module('sqaod.py')
+    if binding == 'cpu':
+        load_reference_cpu(pkg)
+        return pkg
     for name in CEXT:
         full = 'sqaod.cuda.' + name
         if binding == 'glue':
@@ -61,6 +70,18 @@ def assemble(binding):
     return pkg
 
 
+def load_reference_cpu(pkg):
+    """sqaod.cpu = the reference's own package (sqaod/cpu/*.py) over its own glue and CPU library built by `make -C oracle refcpu`."""
+    for name in CPU_CEXT:
+        full = 'sqaod.cpu.' + name
+        spec = importlib.util.spec_from_file_location(full, os.path.join(SUITE, 'glue_cpu', name + '.so'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        sys.modules[full] = mod
+    pkg.cpu = importlib.import_module('sqaod.cpu')
+    return pkg.cpu
+
+
 def main():
     binding = sys.argv[1] if len(sys.argv) > 1 else 'glue'
     if not os.path.isdir(os.path.join(SUITE, 'tests')):
@@ -68,7 +89,8 @@ def main():
         return 0
     assemble(binding)
     import pytest
-    args = [os.path.join(SUITE, 'tests'), '-q', '-p', 'no:cacheprovider', '-k', 'cuda and not version', '--rootdir', SUITE,
+    select = 'not cuda and not version' if binding == 'cpu' else 'cuda and not version'
+    args = [os.path.join(SUITE, 'tests'), '-q', '-p', 'no:cacheprovider', '-k', select, '--rootdir', SUITE,
             '-o', 'python_files=test_*.py', '-rfE', '--tb=short'] + sys.argv[2:]
     rc = pytest.main(args)
     print('REFSUITE_RC %s %d' % (binding, int(rc)))

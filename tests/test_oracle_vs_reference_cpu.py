@@ -1,0 +1,51 @@
+"""The CPU oracle against the REFERENCE ITSELF, run here (no GPU, nothing of the product library).
+
+`make -C oracle refcpu` (build container: /root/reference present) compiles the reference's own CPU back end -- sqaodc/common/*.cpp,
+sqaodc/cpu/*.cpp and the cpu_*.cpp CPython glue, every file unmodified and where it lies -- into oracle/_ref/ (git-ignored, travels with
+the snapshot).  The one dependency this image lacks, Eigen, is replaced by oracle/eigen_standin/Eigen/Core, a small matrix class written
+for this repository; the reference's Metropolis loops do not go through it (own MT19937, own dot_simd), its formulas, the bipartite
+contraction and the brute-force energies do, which is why those comparisons use inputs whose sums are exact.
+
+  1. the reference's own Python test-suite (sqaodpy/tests, CPU and pure-Python classes) passes on that build: the build is sound;
+  2. oracle/oracle.cpp reproduces the compiled reference bit for bit: spins after every annealOneStep (dense and bipartite; colouring
+     serial and OpenMP-parallel, naive, SA; fp32 and fp64; even / odd rings, m = 1, row lengths with a SIMD tail), randomize_spin,
+     Hamiltonians, brute-force minima and solution lists incl. the capped degenerate case, all formulas.
+Without the build (no reference tree at build time) the tests skip."""
+import os
+import re
+import subprocess
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SUITE = os.path.join(ROOT, 'oracle', '_ref', 'refsuite')
+
+
+def _have_build():
+    if os.path.isdir('/root/reference/sqaodc'):
+        subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle'), 'liboracle.so', 'glue', 'refcpu'], stdout=subprocess.DEVNULL)
+    return os.path.exists(os.path.join(SUITE, 'glue_cpu', 'cpu_dg_annealer.so')) and os.path.isdir(os.path.join(SUITE, 'tests'))
+
+
+def test_reference_cpu_build_passes_the_reference_python_suite():
+    if not _have_build():
+        pytest.skip('oracle/_ref reference CPU build absent (run `make -C oracle refcpu` where /root/reference exists)')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'refsuite_runner.py'), 'cpu'], capture_output=True, text=True,
+                         timeout=1500, cwd=SUITE)
+    log = out.stdout[-4000:] + out.stderr[-2000:]
+    m = re.search(r'(\d+) passed', out.stdout)
+    assert m and int(m.group(1)) > 250, log
+    assert 'REFSUITE_RC cpu 0' in out.stdout, log
+
+
+@pytest.mark.parametrize('workers', [1, 3])
+def test_oracle_reproduces_the_compiled_reference(workers):
+    if not _have_build():
+        pytest.skip('oracle/_ref reference CPU build absent (run `make -C oracle refcpu` where /root/reference exists)')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'refcpu_compare.py'), str(workers)], capture_output=True, text=True,
+                         timeout=900)
+    if 'REFCPU_COMPARE_SKIP' in out.stdout:
+        pytest.skip(out.stdout.strip().splitlines()[-1])
+    lines = [l for l in out.stdout.splitlines() if ' ok ' in l or ' DIFF ' in l]
+    assert 'REFCPU_COMPARE_OK workers=%d' % workers in out.stdout, '\n'.join(l for l in lines if 'DIFF' in l) + out.stderr[-2000:]
+    assert len(lines) >= (60 if workers == 1 else 25), len(lines)

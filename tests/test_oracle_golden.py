@@ -175,3 +175,51 @@ def test_bipartite_anneal_reaches_ground_state(oracle):
                 b.anneal_one_step(G, beta)
                 G *= (0.02 / 5.0) ** 0.01
             assert b.get_E().min() == -(N0 * N1 + N0 + N1)
+
+
+# ---- chains recorded from the reference's own compiled CPU annealers (tests/golden/make_golden_refcpu.py, one worker): the oracle's
+# MT19937 mode must walk through exactly the same spins, step after step
+def _chain_keys(prefix):
+    import os
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'refcpu_chains.npz'))
+    return sorted({k.split('/')[0] for k in f.files if k.startswith(prefix)}, key=lambda s: int(s[len(prefix):]))
+
+
+@pytest.fixture(scope='module')
+def refcpu_chains():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'refcpu_chains.npz'))
+
+
+@pytest.mark.parametrize('key', _chain_keys('dense'))
+def test_dense_chain_equals_the_compiled_reference(oracle, refcpu_chains, key):
+    g = refcpu_chains
+    N, m, seed, width = (int(v) for v in g[key + '/meta'])
+    dtype = np.float32 if width == 4 else np.float64
+    ann = oracle.DenseGraphAnnealer(None, 0, dtype, n_trotters=m, algorithm=str(g[key + '/algo']), n_workers=1, rng='mt')
+    ann.set_hamiltonian(g[key + '/h'], g[key + '/J'], dtype(g[key + '/c']))
+    ann.seed(seed); ann.prepare(); ann.randomize_spin()
+    q = g[key + '/q']
+    assert np.array_equal(ann.get_q(), q[0]), 'randomize_spin'
+    for k, G in enumerate(g[key + '/G']):
+        ann.anneal_one_step(float(G), 1. / 0.02)
+        assert np.array_equal(ann.get_q(), q[k + 1]), 'step %d' % k
+    assert np.allclose(ann.get_E(), g[key + '/E'], rtol=2e-5 if width == 4 else 1e-12, atol=1e-4 if width == 4 else 1e-10)
+
+
+@pytest.mark.parametrize('key', _chain_keys('bip'))
+def test_bipartite_chain_equals_the_compiled_reference(oracle, refcpu_chains, key):
+    g = refcpu_chains
+    N0, N1, m, seed, width = (int(v) for v in g[key + '/meta'])
+    dtype = np.float32 if width == 4 else np.float64
+    ann = oracle.BipartiteGraphAnnealer(g[key + '/b0'], g[key + '/b1'], g[key + '/W'], 0, dtype, n_trotters=m,
+                                        algorithm=str(g[key + '/algo']), n_workers=1, rng='mt')
+    ann.seed(seed); ann.prepare(); ann.randomize_spin()
+    q0, q1 = g[key + '/q0'], g[key + '/q1']
+    a, b = ann.get_q()
+    assert np.array_equal(a, q0[0]) and np.array_equal(b, q1[0]), 'randomize_spin'
+    for k, G in enumerate(g[key + '/G']):
+        ann.anneal_one_step(float(G), 1. / 0.02)
+        a, b = ann.get_q()
+        assert np.array_equal(a, q0[k + 1]) and np.array_equal(b, q1[k + 1]), 'step %d' % k
+    assert np.array_equal(ann.get_E(), g[key + '/E'])      # quantised inputs: exact

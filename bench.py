@@ -6,11 +6,15 @@
                                                               on the host cores; the oracle port when that build is absent)
 
 metric  = spin-flip attempts per second (BASELINE.json); one step = one annealOneStep = N*m attempts.
-value   = whole-job attempts/s with the problem resident in HBM, timed with CUDA events on the launching stream, at the
-          reference benchmark's fixed operating point G=0.01, beta=50 (sqaodpy/benchmark/benchmark.py:10-11).
+value   = whole-job attempts/s with the problem resident in HBM, timed with CUDA events on the launching stream, in the reference
+          benchmark's protocol (sqaodpy/benchmark/benchmark.py:9-48): fixed operating point G=0.01, beta=50, randomize_spin, an
+          untimed warm-up of >= 5 s of anneal_one_step at that point (the chain is stationary when the clock starts), then the timed
+          steps.  Here: --equilibrate-seconds of untimed steps, the W warm-up steps, then exactly K timed steps.
 e2e     = the same metric through the public API (sqaod_b200 -> C ABI) with host buffers: every step uploads the spin
           matrix from pinned memory, anneals one step, evaluates the energies and reads spins + energies back.
 Further legs of the same line (SURVEY.md 8d asks for them because the field-mode sweep's cost follows the acceptance rate):
+  transient              the K steps that follow randomize_spin + W warm-up steps WITHOUT the protocol's warm-up phase (acceptance
+                         still falling: the sweep's worst case at this operating point)
   sustained              >= 2 s of back-to-back steps at the fixed point, with its own clock samples
   config.schedule_sweep  a fresh anneal over the reference example's whole schedule G 5 -> 0.01 (geometric), beta = 50
                          (sqaodpy/example/dense_graph_annealer.py:60-70), with the acceptance rate per fifth of the schedule
@@ -313,6 +317,9 @@ def main():
     ap.add_argument('--sweep-mode', default='auto', choices=['auto', 'classic', 'field'],
                     help="how the sweep gets its local fields: 'classic' streams one J row per attempt, 'field' keeps J.q in shared "
                          "memory and streams one row per accepted flip (same Markov chain); 'auto' = the library's choice")
+    ap.add_argument('--equilibrate-seconds', type=float, default=5.0,
+                    help="untimed steps at the operating point before the warm-up and timed steps: the reference protocol's warm-up "
+                         "phase (benchmark.py:17-27, batches of steps until one takes >= 5 s); 0: time right after randomize_spin")
     ap.add_argument('--sustain-seconds', type=float, default=2.5, help='length of the sustained leg (0: skip)')
     ap.add_argument('--schedule-steps', type=int, default=100, help='steps of the G 5 -> 0.01 schedule leg (0: skip)')
     ap.add_argument('--no-classic-leg', action='store_true')
@@ -324,6 +331,7 @@ def main():
     args = ap.parse_args()
     if args.quick:
         args.sustain_seconds, args.schedule_steps, args.no_classic_leg, args.no_comm_legs, args.no_cpu_baseline = 0.0, 0, True, True, True
+        args.equilibrate_seconds = min(args.equilibrate_seconds, 1.0)
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -367,6 +375,30 @@ def main():
         return float(t.item())
 
     attempts_per_step = N * m
+
+    # ---------------- transient: the K steps right after randomize_spin + W warm-up steps (no protocol warm-up phase) ----------------
+    for _ in range(args.warmup):
+        ann.anneal_one_step(G_FIXED, BETA)
+    barrier()
+    t_acc0 = ann.get_stats()['accepted']
+    ms_tr = max_over_ranks(timed_steps(torch, stream, ann, [G_FIXED] * args.steps, BETA, barrier))
+    transient = {'steps': args.steps, 'ms_per_step': ms_tr / args.steps, 'value': world * attempts_per_step * args.steps / (ms_tr * 1e-3),
+                 'unit': 'attempts/s', 'acceptance_rate': (ann.get_stats()['accepted'] - t_acc0) / float(attempts_per_step * args.steps),
+                 'note': 'steps %d..%d after randomize_spin: acceptance still falling' % (args.warmup, args.warmup + args.steps - 1)}
+
+    # ---------------- the reference protocol's warm-up phase: untimed steps at the operating point until the chain is stationary ----------------
+    equil_steps = 0
+    if args.equilibrate_seconds > 0:
+        batch = max(10, int(0.25e3 / max(ms_tr / args.steps, 1e-3)))     # ~0.25 s of steps between clock reads
+        t_eq = time.perf_counter()
+        while True:
+            for _ in range(batch):
+                ann.anneal_one_step(G_FIXED, BETA)
+            torch.cuda.synchronize()
+            equil_steps += batch
+            # every rank sees the same (max over ranks) elapsed time, so all ranks run the same number of batches
+            if max_over_ranks(time.perf_counter() - t_eq) >= args.equilibrate_seconds:
+                break
 
     # ---------------- headline: device-resident throughput at the fixed operating point ----------------
     for _ in range(args.warmup):
@@ -499,6 +531,11 @@ def main():
                                              'streamed per ACCEPTED flip; one accept-chain warp per trotter)' if mode == 'field' else ' (one J row streamed per attempt)'),
                        'l2': 'J is %d MiB > 126 MB L2 and rows are drawn at random, no flush needed' % (N * N * 4 >> 20),
                        'acceptance_rate': acc_rate,
+                       'protocol': 'sqaodpy/benchmark/benchmark.py:9-48: randomize_spin, untimed warm-up phase at the operating point (here %d '
+                                   'steps = %.1f s; the reference: batches until one takes >= 5 s), %d warm-up steps, %d timed steps; the '
+                                   '"transient" leg times the same K steps without the warm-up phase' % (
+                                       equil_steps, args.equilibrate_seconds, args.warmup, args.steps),
+                       'equilibration_steps': equil_steps,
                        'flag_waits': stats1['flag_waits'] - stats0['flag_waits'],
                        'device': {'sms': sms, 'sm_mhz_used_for_cycle_conversion': mhz},
                        # chain warp 0 and field warp 0 of every CTA, averaged: where a step goes
@@ -511,6 +548,7 @@ def main():
                     'steps': e2e_steps, 'E_min': float(np.min(E))},
             'gpu_launches': int(launches),
             'roofline': roofline,
+            'transient': transient,
             'sustained': sustained,
             'classic': classic,
             'comm': comm,

@@ -78,9 +78,39 @@ def bipartite(out, key, N0, N1, m, dtype, algo, seed, steps):
     out[key + '/algo'] = np.asarray(algo)
 
 
+def config_c1(out):
+    """BASELINE.json configs[0] (C1), the reference's tutorial anneal through sqaod.cpu (sqaodpy/example/dense_graph_annealer.py:22-70):
+    N = 128, m = 32, fp64, seed 13255, G = 5 -> 0.01 with G *= 0.99 (619 steps), beta = 1/0.02; W ~ U(-0.5, 0.5) symmetric, not
+    quantised.  Spins recorded every 124 steps and at the end; QUBO -> Ising goes through set_hamiltonian as above."""
+    N, m, beta, dtype = 128, 32, 1. / 0.02, np.float64
+    rng = np.random.default_rng(13255)
+    A = rng.random((N, N)) - 0.5
+    W = np.triu(A) + np.triu(A, 1).T
+    J = (-0.25 * W).astype(dtype)
+    np.fill_diagonal(J, 0)
+    h = (-0.5 * W.sum(axis=0)).astype(dtype)
+    c = dtype(0.25 * W.sum())
+    ann = sq.cpu.dense_graph_annealer(dtype=dtype, algorithm=sq.algorithm.coloring)
+    ann.set_hamiltonian(h, J, c)
+    ann.set_preferences(n_trotters=m)
+    ann.seed(13255); ann.prepare(); ann.randomize_spin()
+    G, k, snaps, at = 5.0, 0, [], []
+    while 0.01 <= G:
+        ann.anneal_one_step(G, beta)
+        G *= 0.99
+        k += 1
+        if k % 124 == 0:
+            snaps.append(np.asarray(ann.get_q(), np.int8)); at.append(k)
+    snaps.append(np.asarray(ann.get_q(), np.int8)); at.append(k)
+    out['c1/h'], out['c1/J'], out['c1/c'] = h, J, np.asarray(c)
+    out['c1/q'], out['c1/at'], out['c1/E'] = np.asarray(snaps), np.asarray(at), np.asarray(ann.get_E())
+    out['c1/steps'] = np.asarray(k)
+
+
 def main():
     A = sq.algorithm
     out = {}
+    config_c1(out)
     k = 0
     for dtype in (np.float32, np.float64):
         for (N, m, algo, steps) in ((40, 10, A.coloring, 4), (33, 7, A.coloring, 4), (130, 4, A.coloring, 3), (24, 6, A.naive, 3),

@@ -223,3 +223,24 @@ def test_bipartite_chain_equals_the_compiled_reference(oracle, refcpu_chains, ke
         a, b = ann.get_q()
         assert np.array_equal(a, q0[k + 1]) and np.array_equal(b, q1[k + 1]), 'step %d' % k
     assert np.array_equal(ann.get_E(), g[key + '/E'])      # quantised inputs: exact
+
+
+def test_config_c1_chain_equals_the_compiled_reference(oracle, refcpu_chains):
+    """BASELINE.json configs[0]: the reference's tutorial anneal (N = 128, m = 32, fp64, G 5 -> 0.01 with G *= 0.99, 619 steps,
+    sqaodpy/example/dense_graph_annealer.py:22-70) as sqaod.cpu ran it -- 2.5 million attempts later the oracle holds the same spins."""
+    g = refcpu_chains
+    ann = oracle.DenseGraphAnnealer(None, 0, np.float64, n_trotters=32, algorithm='coloring', n_workers=1, rng='mt')
+    ann.set_hamiltonian(g['c1/h'], g['c1/J'], np.float64(g['c1/c']))
+    ann.seed(13255); ann.prepare(); ann.randomize_spin()
+    at = [int(v) for v in g['c1/at']]
+    G, k, i = 5.0, 0, 0
+    while 0.01 <= G:
+        ann.anneal_one_step(G, 1. / 0.02)
+        G *= 0.99
+        k += 1
+        if k % 124 == 0:
+            assert at[i] == k and np.array_equal(ann.get_q(), g['c1/q'][i]), 'step %d' % k
+            i += 1
+    assert k == int(g['c1/steps']) == 619
+    assert np.array_equal(ann.get_q(), g['c1/q'][-1])
+    assert np.allclose(ann.get_E(), g['c1/E'], rtol=1e-12, atol=1e-10)

@@ -208,6 +208,40 @@ def formulas_case(dtype, grid):
     report(name, bool(ok))
 
 
+# ------------------------------------------------------------------ the north star's statistical criterion, on the CPU
+def statistics_case(N, m, steps, algo, nseeds=256):
+    """The B200 sweep walks the oracle's Philox-mode chain bit for bit (GPU exact-chain tests), and the RNG streams of the two solvers
+    differ by design -- so annealer output is judged statistically (BASELINE.json): over 256 seeds the final-energy distribution and
+    the ground-state hit rate of the Philox chain must be indistinguishable from those of the reference's own sqaod.cpu annealer.
+    Same thresholds as tests/test_annealer_statistics_gpu.py."""
+    from scipy import stats
+    rng = np.random.default_rng(2024 + N)
+    W = sym(rng, N, 16384).astype(np.float32)
+    beta = 1. / 0.02
+    sa = algo.startswith('sa')
+    G0, G1 = (2.0, 0.02) if sa else (5.0, 0.01)
+    Gs = [G0 * (G1 / G0) ** (k / float(steps)) for k in range(steps)]
+    e_ph, e_ref = np.empty(nseeds), np.empty(nseeds)
+    ref = sq.cpu.dense_graph_annealer(W, sq.minimize, np.float32, n_trotters=m, algorithm=algo)
+    for s in range(nseeds):
+        ref.seed(s); ref.prepare(); ref.randomize_spin()
+        mine = orc.DenseGraphAnnealer(W, 0, np.float32, n_trotters=m, algorithm=algo, n_workers=1, rng='philox')
+        mine.seed(s); mine.prepare(); mine.randomize_spin()
+        for G in Gs:
+            ref.anneal_one_step(G, beta); mine.anneal_one_step(G, beta)
+        e_ref[s] = np.min(ref.get_E()); e_ph[s] = mine.get_E().min()
+    ground = min(e_ph.min(), e_ref.min())
+    tol = 2e-5 * max(1.0, abs(ground))
+    hit_p, hit_r = float((e_ph <= ground + tol).mean()), float((e_ref <= ground + tol).mean())
+    p = 0.5 * (hit_p + hit_r)
+    sigma = max(np.sqrt(2 * p * (1 - p) / nseeds), 1e-3)
+    ks = stats.ks_2samp(np.round(e_ph / tol) * tol, np.round(e_ref / tol) * tol).pvalue
+    se = np.sqrt(e_ph.var() / nseeds + e_ref.var() / nseeds) + 1e-9
+    ok = abs(hit_p - hit_r) < 4 * sigma and ks > 1e-3 and abs(e_ph.mean() - e_ref.mean()) < 4 * se + tol
+    report('statistics over %d seeds, dense %s N=%d m=%d %d steps: Philox chain vs sqaod.cpu' % (nseeds, algo, N, m, steps), bool(ok),
+           'hit rate %.3f vs %.3f, KS p = %.3f, mean %.4f vs %.4f' % (hit_p, hit_r, ks, e_ph.mean(), e_ref.mean()))
+
+
 def main():
     A = sq.algorithm
     for dtype in (np.float32, np.float64):
@@ -235,6 +269,10 @@ def main():
             bipartite_bf_case(7, 4, dtype, 1)
             formulas_case(dtype, 64)
             formulas_case(dtype, 0)
+    if WORKERS == 1:
+        statistics_case(24, 4, 4, A.coloring)
+        statistics_case(64, 16, 20, A.coloring)
+        statistics_case(48, 8, 12, A.sa_naive)
     if FAILED:
         print('REFCPU_COMPARE_FAILED %d: %s' % (len(FAILED), '; '.join(FAILED)))
         return 1

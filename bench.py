@@ -19,6 +19,8 @@ Further legs of the same line (SURVEY.md 8d asks for them because the field-mode
   config.schedule_sweep  a fresh anneal over the reference example's whole schedule G 5 -> 0.01 (geometric), beta = 50
                          (sqaodpy/example/dense_graph_annealer.py:60-70), with the acceptance rate per fifth of the schedule
   classic                the one-J-row-per-attempt kernel (HBM-bound) on the same state
+  secondary              the tensor-core rows on one GPU: calculate_E at C2 and the bipartite annealOneStep at C3 (N0=N1=4096, m=512), with
+                         their tensor roofline (algorithmic flops / time against the measured dense-bf16 peak / 3)
   comm                   what communicates: brute force N=40 sharded over the ranks + NCCL min/gather merge,
                          the ring-sharded N=32768 sweep (256 trotters per GPU, NVLink hand-off), 512 replicas per GPU of N=1024 m=128
 At N > 1 every GPU anneals its own replica of the headline problem with its own seed ("replicas only"): scaling weak.
@@ -89,6 +91,17 @@ def measured_peaks():
         d = json.load(open(p))
         return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def measured_tensor_peak():
+    """dense bf16 TFLOP/s of this pool's B200s (burst figure: the kernels below are timed alone, a few launches each)"""
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['bf16_tflops']), 'measured (MEASURED_PEAKS.json bf16_tflops)'
+        except Exception:
+            pass
+    return 2250.0, 'fallback (B200_PROFILING.md nominal dense bf16)'
 
 
 def ncu_traffic_note(mode):
@@ -305,6 +318,59 @@ def comm_legs(args, torch, dist, sq, dev, rank, local_rank, world, barrier):
     return out
 
 
+def secondary_legs(args, torch, sq, dev, stream, ann, rank):
+    """The tensor-core rows of the path (a6, a7) on one GPU, so that they have a driver-side number next to the
+    headline: calculate_E at C2 (on the headline annealer's state) and the bipartite annealOneStep at C3, both through the split-bf16
+    tcgen05 spin GEMM.  Tensor roofline: algorithmic flops (the three bf16 passes of the split are NOT counted as extra
+    flops) / time against the measured dense-bf16 peak / 3."""
+    out = {}
+    peak, peak_src = measured_tensor_peak()
+
+    def timed(fn, reps, warm):      # per-GPU figures (rank 0's is printed): no collective in here, so a failure on one rank cannot hang the others
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def tensor_roofline(flops, ms):
+        tf = flops / (ms * 1e-3) / 1e12
+        return {'bound': 'tensor', 'achieved': tf, 'peak': peak / 3.0, 'unit': 'TFLOP/s', 'frac': tf / (peak / 3.0), 'peak_source': peak_src,
+                'note': 'algorithmic flops / time; peak = dense bf16 peak / 3 (split-precision GEMM: hi + mid + lo planes of J, one pass each)'}
+    try:    # a7: E_y = -c - h.q_y - q_y^T J q_y for all m trotters (GEMM m x N x N + row dots), result left on the device (async read-back)
+        N, m = args.N, args.m
+        ms = timed(ann.calculate_E, 10, 2)
+        flops = 2.0 * m * N * N + 4.0 * m * N
+        out['calculate_E_c2'] = {'N': N, 'm': m, 'ms': ms, 'algorithmic_flops': flops, 'kernel': 'tcSpinGemmKernel (tcgen05, bf16 x 3) + row-dot',
+                                 'roofline': tensor_roofline(flops, ms)}
+    except Exception as e:
+        out['calculate_E_c2'] = {'error': str(e)[:300]}
+    try:    # a6: C3, one step = two half steps, each dEmat = qFixed . J(^T) on the tensor cores + one fused coloured flip launch
+        N0 = N1 = args.bipartite_N
+        mb = args.m
+        rng = np.random.default_rng(W_SEED + 3)
+        b0 = rng.random(N0, dtype=np.float32) - np.float32(0.5)
+        b1 = rng.random(N1, dtype=np.float32) - np.float32(0.5)
+        Wb = rng.random((N1, N0), dtype=np.float32) - np.float32(0.5)
+        bg = sq.bipartite_graph_annealer(b0, b1, Wb, sq.minimize, np.float32, n_trotters=mb, device=dev)
+        bg.seed(2000 + rank); bg.prepare(); bg.randomize_spin()
+        ms = timed(lambda: bg.anneal_one_step(G_FIXED, BETA), 50, 5)
+        flops = 4.0 * mb * N0 * N1
+        out['bipartite_c3'] = {'N0': N0, 'N1': N1, 'm': mb, 'ms_per_step': ms, 'attempts_per_s': (N0 + N1) * mb / (ms * 1e-3),
+                               'algorithmic_flops_per_step': flops, 'E_min': float(np.min(bg.get_E())),
+                               'kernels': 'per half step: tcSpinGemmKernel (tcgen05, bf16 x 3) + bgFlipFusedKernel',
+                               'roofline': tensor_roofline(flops, ms)}
+        del bg
+    except Exception as e:
+        out['bipartite_c3'] = {'error': str(e)[:300]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -324,6 +390,8 @@ def main():
     ap.add_argument('--schedule-steps', type=int, default=100, help='steps of the G 5 -> 0.01 schedule leg (0: skip)')
     ap.add_argument('--no-classic-leg', action='store_true')
     ap.add_argument('--no-comm-legs', action='store_true', help='skip the brute-force / ring / replica legs')
+    ap.add_argument('--no-secondary-legs', action='store_true', help='skip the calculate_E / bipartite (tensor-core) legs')
+    ap.add_argument('--bipartite-N', type=int, default=4096, help='N0 = N1 of the bipartite leg (C3: 4096)')
     ap.add_argument('--bf-N', type=int, default=40)
     ap.add_argument('--ring-N', type=int, default=32768)
     ap.add_argument('--replicas-per-gpu', type=int, default=512)
@@ -332,6 +400,7 @@ def main():
     if args.quick:
         args.sustain_seconds, args.schedule_steps, args.no_classic_leg, args.no_comm_legs, args.no_cpu_baseline = 0.0, 0, True, True, True
         args.equilibrate_seconds = min(args.equilibrate_seconds, 1.0)
+        args.no_secondary_legs = True
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -485,6 +554,13 @@ def main():
                    'algorithmic_bytes_per_launch': attempts_per_step * N * 4}
         del ann_c
 
+    secondary = None
+    if not args.no_secondary_legs:
+        try:
+            secondary = secondary_legs(args, torch, sq, dev, stream, ann, rank)
+        except Exception as e:      # reported numbers, never a reason to lose the line
+            secondary = {'error': str(e)[:300]}
+
     comm = None
     if not args.no_comm_legs:
         comm = comm_legs(args, torch, dist, sq, dev, rank, local_rank, world, barrier)
@@ -551,6 +627,7 @@ def main():
             'transient': transient,
             'sustained': sustained,
             'classic': classic,
+            'secondary': secondary,
             'comm': comm,
         }
         if world == 1 and not args.no_cpu_baseline:

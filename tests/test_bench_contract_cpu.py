@@ -28,6 +28,7 @@ class _FakeAnnealer(object):
     def anneal_one_step(self, G, beta): self.steps += 1
     def set_qset(self, q): pass
     def get_E(self): return np.full(self.m, -1.0, np.float32)
+    def calculate_E(self): pass
 
     def get_spins(self, out=None):
         if out is not None:
@@ -75,6 +76,7 @@ def _install_fakes(monkeypatch):
     sq.Device = Device
     sq.set_active_device = lambda d: None
     sq.dense_graph_annealer = lambda W, opt, dtype, n_trotters=None, device=None: _FakeAnnealer(0 if W is None else W.shape[0], n_trotters or 1)
+    sq.bipartite_graph_annealer = lambda b0, b1, W, opt, dtype, n_trotters=None, device=None: _FakeAnnealer(W.shape[1], n_trotters or 1)
     mg = types.ModuleType('sqaod_b200.multigpu')
     mg.sharded_dense_bf_search = lambda W, opt, dtype: (np.float32(-1.5), [np.zeros(W.shape[0], np.int8)])
     mg.anneal_replicas = lambda W, R, Gs, beta, dtype, n_trotters=None: (-2.0, None, None, None)
@@ -104,9 +106,9 @@ def _run(monkeypatch, argv):
 def test_bench_line_carries_the_contract_keys(monkeypatch):
     line = _run(monkeypatch, ['--gpus', '1', '--steps', '4', '--warmup', '5', '--N', '64', '--m', '8', '--no-cpu-baseline',
                               '--equilibrate-seconds', '0.05', '--sustain-seconds', '0.01', '--schedule-steps', '10', '--bf-N', '12', '--ring-N', '256',
-                              '--replicas-per-gpu', '2'])
+                              '--replicas-per-gpu', '2', '--bipartite-N', '32'])
     for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data',
-              'config', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'transient', 'sustained', 'classic', 'comm'):
+              'config', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'transient', 'sustained', 'classic', 'secondary', 'comm'):
         assert k in line, k
     assert line['steps'] == 4 and line['warmup'] == 5 and line['n_gpus'] == 1 and line['vs_baseline'] is None
     assert line['ms_per_step'] == pytest.approx(7.0 / 4)                     # the stand-in clock advances 7 ms per event
@@ -116,12 +118,15 @@ def test_bench_line_carries_the_contract_keys(monkeypatch):
     assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
     assert line['config']['equilibration_steps'] > 0 and 'workload' in line['config'] and line['config']['schedule_sweep']['steps'] == 10
     assert line['transient']['steps'] == 4
+    for leg in ('calculate_E_c2', 'bipartite_c3'):
+        assert 'error' not in line['secondary'][leg], line['secondary'][leg]
+        assert line['secondary'][leg]['roofline']['bound'] == 'tensor' and line['secondary'][leg]['roofline']['frac'] > 0
     assert 'error' not in line['comm']['bf_n40_sharded'] and 'error' not in line['comm']['replicas_c5a'] and 'error' not in line['comm']['ring_c5b']
 
 
 def test_quick_mode_and_reference_arm_keys(monkeypatch):
     line = _run(monkeypatch, ['--quick', '--steps', '3', '--N', '64', '--m', '8'])
-    assert line['sustained'] is None and line['classic'] is None and line['comm'] is None and 'cpu_baseline' not in line
+    assert line['sustained'] is None and line['classic'] is None and line['comm'] is None and line['secondary'] is None and 'cpu_baseline' not in line
     import bench
     monkeypatch.setattr(bench, 'N_SPINS', 256)
     monkeypatch.setattr(bench, 'M_TROTTERS', 16)

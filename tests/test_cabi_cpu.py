@@ -1,8 +1,11 @@
 """CPU-side checks of the product library: it loads, exports every symbol include/sqaod_b200.h declares, keeps the
 reference's host-side semantics (preferences, state machine errors) and fails loudly without a device.  No compute."""
 import ctypes as C
+import os
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope='module')
@@ -89,3 +92,42 @@ def test_python_helpers_match_the_reference():
     assert x.tolist() == [[0, 1, 0, 1], [0, 0, 1, 0]]
     assert int(sq.minimize) == 0 and int(sq.maximize) == 1
     assert sq.algorithm.is_sqa('coloring') and not sq.algorithm.is_sqa('sa_naive')
+
+
+def test_preference_and_algorithm_names_equal_the_reference_library():
+    """The name tables of the solver API (sqaodc/common/Preference.cpp:8-100): `sqaod::algorithmToString / FromString`,
+    `preferenceNameToString / FromString` and `isSQAAlgorithm` of libsqaod_b200.so against the same functions of the reference's own CPU
+    library, compiled from its sources (oracle/_ref/libsqaodc_refcpu.so; `make -C oracle refcpu`), for every enum value and every name
+    -- plus unknown inputs.  Plain functions over ints and C strings: no device, no objects cross the two libraries."""
+    import ctypes as C
+    ref_so = os.path.join(ROOT, 'oracle', '_ref', 'libsqaodc_refcpu.so')
+    if not os.path.exists(ref_so):
+        pytest.skip('reference CPU library not built (run `make -C oracle refcpu` where /root/reference exists)')
+    ours, ref = C.CDLL(os.path.join(ROOT, 'sqaod_b200', 'lib', 'libsqaod_b200.so')), C.CDLL(ref_so)
+    sym = {'a2s': '_ZN5sqaod17algorithmToStringENS_9AlgorithmE', 's2a': '_ZN5sqaod19algorithmFromStringEPKc',
+           'p2s': '_ZN5sqaod22preferenceNameToStringENS_14PreferenceNameE', 's2p': '_ZN5sqaod24preferenceNameFromStringEPKc',
+           'sqa': '_ZN5sqaod14isSQAAlgorithmENS_9AlgorithmE'}
+
+    def fn(lib, key, restype, argtype):
+        f = getattr(lib, sym[key])
+        f.restype, f.argtypes = restype, [argtype]
+        return f
+    for lib_pair in [(ours, ref)]:
+        a2s = [fn(l, 'a2s', C.c_char_p, C.c_int) for l in lib_pair]
+        s2a = [fn(l, 's2a', C.c_int, C.c_char_p) for l in lib_pair]
+        p2s = [fn(l, 'p2s', C.c_char_p, C.c_int) for l in lib_pair]
+        s2p = [fn(l, 's2p', C.c_int, C.c_char_p) for l in lib_pair]
+        sqa = [fn(l, 'sqa', C.c_bool, C.c_int) for l in lib_pair]
+    names = set()
+    for v in range(0, 9):                      # enum Algorithm, Preference.h:8-17
+        a, b = a2s[0](v), a2s[1](v)
+        assert a == b, (v, a, b)
+        assert sqa[0](v) == sqa[1](v), v
+        names.add(a)
+    for v in list(range(0, 8)) + [100]:        # enum PreferenceName, Preference.h:26-36
+        a, b = p2s[0](v), p2s[1](v)
+        assert a == b, (v, a, b)
+        names.add(a)
+    for s in sorted(n for n in names if n) + [b'', b'nonsense', b'Coloring', b'tile_size', b'n_trotters', b'sa_naive', b'default']:
+        assert s2a[0](s) == s2a[1](s), s
+        assert s2p[0](s) == s2p[1](s), s

@@ -41,6 +41,12 @@ class _FakeAnnealer(object):
                 'chain_wait_rows_cycles': 100 * self.steps, 'chain_wait_neighbour_cycles': 50 * self.steps, 'barrier_cycles_dot': 500 * self.steps}
 
 
+class _Patcher(object):
+    """the two calls of pytest's monkeypatch that _install_fakes uses, for the worker processes of the two-rank run"""
+    def setattr(self, obj, name, value): setattr(obj, name, value)
+    def setitem(self, mapping, key, value): mapping[key] = value
+
+
 def _install_fakes(monkeypatch):
     import torch
     clock = {'ms': 0.0}
@@ -80,6 +86,15 @@ def _install_fakes(monkeypatch):
     mg = types.ModuleType('sqaod_b200.multigpu')
     mg.sharded_dense_bf_search = lambda W, opt, dtype: (np.float32(-1.5), [np.zeros(W.shape[0], np.int8)])
     mg.anneal_replicas = lambda W, R, Gs, beta, dtype, n_trotters=None: (-2.0, None, None, None)
+
+    class RingShardedDenseAnnealer(object):
+        def __init__(self, problem, optimize, dtype, n_trotters=None):
+            self.ann = _FakeAnnealer(problem[1], n_trotters)
+        def seed(self, s): pass
+        def prepare(self): pass
+        def randomize_spin(self): pass
+        def anneal_one_step(self, G, beta): self.ann.anneal_one_step(G, beta)
+    mg.RingShardedDenseAnnealer = RingShardedDenseAnnealer
     sq.multigpu = mg
     monkeypatch.setitem(sys.modules, 'sqaod_b200', sq)
     monkeypatch.setitem(sys.modules, 'sqaod_b200.multigpu', mg)
@@ -138,3 +153,52 @@ def test_quick_mode_and_reference_arm_keys(monkeypatch):
     assert ref['impl'] == 'reference' and ref['steps'] == 2 and ref['cpu_baseline']['kind'] in ('reference', 'port')
     assert ref['e2e'] == {'value': ref['value'], 'unit': 'attempts/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert ref['cpu_baseline']['cores'] >= 1 and ref['value'] > 0
+
+
+def _worker():
+    """one rank of the two-rank dry run: the same stand-ins, torch.distributed over gloo instead of NCCL"""
+    import torch
+    import torch.distributed as dist
+    _install_fakes(_Patcher())
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, **kw: real_init('gloo')
+    sys.path.insert(0, ROOT)
+    import bench
+    bench.ClockSampler.start = lambda self: None
+    bench.ClockSampler.stop = lambda self: {'sm_mhz': 1965.0, 'sm_max_mhz': 1965.0, 'reasons': [], 'samples': 3}
+    sys.argv = ['bench.py', '--gpus', '2', '--steps', '4', '--warmup', '3', '--N', '64', '--m', '8', '--equilibrate-seconds', '0.05',
+                '--sustain-seconds', '0.01', '--schedule-steps', '10', '--bf-N', '12', '--ring-N', '256', '--replicas-per-gpu', '2', '--bipartite-N', '32']
+    bench.main()
+
+
+def test_two_rank_run_does_not_deadlock():
+    """every collective of bench.py is reached by both ranks the same number of times (world size 2, gloo, 127.0.0.1)"""
+    import socket
+    import subprocess
+    with socket.socket() as so:
+        so.bind(('127.0.0.1', 0))
+        port = so.getsockname()[1]
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), '--worker'], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=300))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    assert [p.returncode for p in procs] == [0, 0], outs[0][1][-1500:] + outs[1][1][-1500:]
+    lines = [l for l in outs[0][0].splitlines() if l.startswith('{')]
+    assert len(lines) == 1 and not [l for l in outs[1][0].splitlines() if l.startswith('{')]      # rank 0 alone prints the line
+    line = json.loads(lines[0])
+    assert line['n_gpus'] == 2 and line['scaling'] == 'weak' and 'cpu_baseline' not in line
+    assert line['value'] == pytest.approx(2 * 64 * 8 * 4 / 7e-3)                                 # whole-job aggregate over both ranks
+    assert 'error' not in line['comm']['ring_c5b'] and line['comm']['ring_c5b']['m'] == 512
+
+
+if __name__ == '__main__' and '--worker' in sys.argv:
+    _worker()

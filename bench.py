@@ -395,6 +395,9 @@ def main():
     ap.add_argument('--bf-N', type=int, default=40)
     ap.add_argument('--ring-N', type=int, default=32768)
     ap.add_argument('--replicas-per-gpu', type=int, default=512)
+    ap.add_argument('--leg-timeout', type=float, default=420.0,
+                    help='seconds any one of the extra legs (sustained, schedule, classic, secondary, comm, cpu_baseline) may take before the '
+                         'line is printed without it')
     ap.add_argument('--quick', action='store_true', help='headline + e2e legs only')
     args = ap.parse_args()
     if args.quick:
@@ -499,78 +502,14 @@ def main():
     torch.cuda.synchronize()
     e2e_value = world * attempts_per_step * e2e_steps / max_over_ranks(time.perf_counter() - t0)
 
-    # ---------------- sustained: >= 2 s back to back, own clock samples (power-cap behaviour on record) ----------------
-    sustained = None
-    if args.sustain_seconds > 0:
-        n_sus = int(max(args.steps, np.ceil(args.sustain_seconds * 1e3 / (ms / args.steps))))
-        sampler2 = ClockSampler(local_rank)
-        if rank == 0:
-            sampler2.start()
-        ms_sus = timed_steps(torch, stream, ann, [G_FIXED] * n_sus, BETA, barrier)
-        clocks2 = sampler2.stop() if rank == 0 else None
-        ms_sus_max = max_over_ranks(ms_sus)
-        sustained = {'steps': n_sus, 'seconds': ms_sus_max * 1e-3, 'ms_per_step': ms_sus_max / n_sus,
-                     'value': world * attempts_per_step * n_sus / (ms_sus_max * 1e-3), 'unit': 'attempts/s', 'clocks': clocks2}
-
-    # ---------------- the whole annealing schedule: G 5 -> 0.01 geometric, beta = 50, from random spins ----------------
-    schedule = None
-    if args.schedule_steps > 0:
-        S = args.schedule_steps
-        Gs = [5.0 * (0.01 / 5.0) ** (k / float(S - 1)) for k in range(S)]
-        ann.randomize_spin()
-        parts, tot_ms, tot_acc = [], 0.0, 0
-        n_part = 5
-        for i in range(n_part):
-            chunk = Gs[i * S // n_part:(i + 1) * S // n_part]
-            a0 = ann.get_stats()['accepted']
-            ms_c = max_over_ranks(timed_steps(torch, stream, ann, chunk, BETA, barrier))
-            acc = ann.get_stats()['accepted'] - a0
-            parts.append({'G_from': chunk[0], 'G_to': chunk[-1], 'steps': len(chunk), 'ms_per_step': ms_c / len(chunk),
-                          'acceptance_rate': acc / float(attempts_per_step * len(chunk))})
-            tot_ms += ms_c
-            tot_acc += acc
-        schedule = {'protocol': 'randomize_spin, then G = 5 -> 0.01 geometric over %d steps at beta = 50 (the range of '
-                                'sqaodpy/example/dense_graph_annealer.py:60-70)' % S,
-                    'steps': S, 'ms_per_step': tot_ms / S, 'value': world * attempts_per_step * S / (tot_ms * 1e-3), 'unit': 'attempts/s',
-                    'acceptance_rate': tot_acc / float(attempts_per_step * S), 'by_fifth': parts, 'E_min_final': float(np.min(ann.get_E()))}
-
-    # ---------------- the classic (one J row per attempt, HBM-bound) kernel on the equilibrated state ----------------
-    classic = None
-    if not args.no_classic_leg and mode != 'classic':
-        q_now = ann.get_spins()
-        ann_c = sq.dense_graph_annealer(W, sq.minimize, np.float32, n_trotters=m, device=dev)
-        ann_c.seed(1000 + rank)
-        ann_c.set_sweep_mode('classic')
-        ann_c.prepare()
-        ann_c.set_qset(q_now)
-        for _ in range(2):
-            ann_c.anneal_one_step(G_FIXED, BETA)
-        n_c = 6
-        c0 = ann_c.get_stats()['accepted']
-        ms_c = max_over_ranks(timed_steps(torch, stream, ann_c, [G_FIXED] * n_c, BETA, barrier))
-        acc_c = ann_c.get_stats()['accepted'] - c0
-        classic = {'ms_per_step': ms_c / n_c, 'value': world * attempts_per_step * n_c / (ms_c * 1e-3), 'unit': 'attempts/s', 'steps': n_c,
-                   'acceptance_rate': acc_c / float(attempts_per_step * n_c), 'kernel': 'denseSweepKernel<float,true,16,false>',
-                   'algorithmic_bytes_per_launch': attempts_per_step * N * 4}
-        del ann_c
-
-    secondary = None
-    if not args.no_secondary_legs:
-        try:
-            secondary = secondary_legs(args, torch, sq, dev, stream, ann, rank)
-        except Exception as e:      # reported numbers, never a reason to lose the line
-            secondary = {'error': str(e)[:300]}
-
-    comm = None
-    if not args.no_comm_legs:
-        comm = comm_legs(args, torch, dist, sq, dev, rank, local_rank, world, barrier)
-
+    # ---------------- the line so far (rank 0): headline, e2e, roofline.  The legs below only add to it ----------------
+    line = {}
+    peak, peak_src = measured_peaks()
+    algo_bytes = attempts_per_step * N * 4              # one J row per attempt
     if rank == 0:
-        peak, peak_src = measured_peaks()
         sms, mhz = device_facts(torch, local_rank, clocks)
         ctas = min(sms, m)
         step_s = ms / args.steps * 1e-3
-        algo_bytes = attempts_per_step * N * 4          # one J row per attempt
         accepted = stats1['accepted'] - stats0['accepted']
         acc_rate = accepted / float(attempts_per_step * args.steps)
         cyc_ms = lambda key: (stats1[key] - stats0[key]) / float(ctas) / (mhz * 1e3) / args.steps
@@ -592,11 +531,6 @@ def main():
                     'note': 'achieved/frac: bytes the kernel moves per launch / launch time / measured copy peak.  algorithmic_*: the SURVEY 8d '
                             'figure (one J row per attempt); in field mode rows of rejected attempts are never fetched, so algorithmic_speedup '
                             '> 1 is an algorithmic gain, not bandwidth'}
-        if classic:
-            cs = classic['ms_per_step'] * 1e-3
-            classic['roofline'] = {'bound': 'hbm', 'achieved': algo_bytes / cs / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': algo_bytes / cs / 1e9 / peak,
-                                   'note': 'algorithmic bytes (one row per attempt) / time; the share that misses L2 is in profiles/ (ncu)',
-                                   'traffic_ncu': ncu_traffic_note('classic')}
         line = {
             'metric': 'spin-flip attempts/sec (dense SQA N=8192 m=512)', 'value': value, 'unit': 'attempts/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
@@ -618,25 +552,124 @@ def main():
                        'ms_per_step_per_cta': {'chain_busy': cyc_ms('barrier_cycles_chain'), 'chain_wait_fields': cyc_ms('chain_wait_rows_cycles'),
                                                'chain_wait_neighbour_ctas': cyc_ms('chain_wait_neighbour_cycles'),
                                                'field_warp_busy': cyc_ms('barrier_cycles_dot')},
-                       'schedule_sweep': schedule},
+                       'schedule_sweep': None},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'attempts/s', 'h2d_bytes_per_step': m * N, 'd2h_bytes_per_step': m * N + m * 4,
                     'steps': e2e_steps, 'E_min': float(np.min(E))},
             'gpu_launches': int(launches),
             'roofline': roofline,
             'transient': transient,
-            'sustained': sustained,
-            'classic': classic,
-            'secondary': secondary,
-            'comm': comm,
+            'sustained': None,
+            'classic': None,
+            'secondary': None,
+            'comm': None,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                v, cores, sample, _, kind = cpu_reference_run(3, 1, budget_s=12.0, max_total_s=15.0)
-                line['cpu_baseline'] = {'value': v, 'unit': 'attempts/s', 'cores': cores, 'kind': kind, 'sample': sample}
-            except Exception as e:      # the baseline is a reported number, never a reason to lose the GPU line
-                line['cpu_baseline'] = {'value': None, 'unit': 'attempts/s', 'cores': None, 'kind': 'port', 'sample': 'failed: %s' % e}
-        print(json.dumps(line), flush=True)
+
+    # The legs below are reported extras.  None of them may cost the line: an exception is recorded in the leg, and if a leg does not
+    # come back within --leg-timeout seconds (a rank lost inside a collective, a kernel that never ends) the watchdog prints the line
+    # as it stands and ends the process.
+    emitted = threading.Lock()
+    leg_now = ['(none)']
+
+    def emit():
+        if rank == 0 and emitted.acquire(False):
+            print(json.dumps(line), flush=True)
+
+    def on_timeout():
+        if rank == 0:
+            line['watchdog'] = 'leg "%s" did not finish within %.0f s; the line was printed without it' % (leg_now[0], args.leg_timeout)
+        emit()
+        os._exit(0)
+
+    def run_leg(name, fn):
+        leg_now[0] = name
+        dog = threading.Timer(args.leg_timeout, on_timeout)
+        dog.daemon = True
+        dog.start()
+        try:
+            return fn()
+        except Exception as e:
+            return {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
+        finally:
+            dog.cancel()
+
+    # ---------------- sustained: >= 2 s back to back, own clock samples (power-cap behaviour on record) ----------------
+    def leg_sustained():
+        n_sus = int(max(args.steps, np.ceil(args.sustain_seconds * 1e3 / (ms / args.steps))))
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        ms_sus = timed_steps(torch, stream, ann, [G_FIXED] * n_sus, BETA, barrier)
+        clocks2 = sampler2.stop() if rank == 0 else None
+        ms_sus_max = max_over_ranks(ms_sus)
+        return {'steps': n_sus, 'seconds': ms_sus_max * 1e-3, 'ms_per_step': ms_sus_max / n_sus,
+                'value': world * attempts_per_step * n_sus / (ms_sus_max * 1e-3), 'unit': 'attempts/s', 'clocks': clocks2}
+    if args.sustain_seconds > 0:
+        line['sustained'] = run_leg('sustained', leg_sustained)
+
+    # ---------------- the whole annealing schedule: G 5 -> 0.01 geometric, beta = 50, from random spins ----------------
+    def leg_schedule():
+        S = args.schedule_steps
+        Gs = [5.0 * (0.01 / 5.0) ** (k / float(S - 1)) for k in range(S)]
+        ann.randomize_spin()
+        parts, tot_ms, tot_acc = [], 0.0, 0
+        n_part = 5
+        for i in range(n_part):
+            chunk = Gs[i * S // n_part:(i + 1) * S // n_part]
+            a0 = ann.get_stats()['accepted']
+            ms_c = max_over_ranks(timed_steps(torch, stream, ann, chunk, BETA, barrier))
+            acc = ann.get_stats()['accepted'] - a0
+            parts.append({'G_from': chunk[0], 'G_to': chunk[-1], 'steps': len(chunk), 'ms_per_step': ms_c / len(chunk),
+                          'acceptance_rate': acc / float(attempts_per_step * len(chunk))})
+            tot_ms += ms_c
+            tot_acc += acc
+        return {'protocol': 'randomize_spin, then G = 5 -> 0.01 geometric over %d steps at beta = 50 (the range of '
+                            'sqaodpy/example/dense_graph_annealer.py:60-70)' % S,
+                'steps': S, 'ms_per_step': tot_ms / S, 'value': world * attempts_per_step * S / (tot_ms * 1e-3), 'unit': 'attempts/s',
+                'acceptance_rate': tot_acc / float(attempts_per_step * S), 'by_fifth': parts, 'E_min_final': float(np.min(ann.get_E()))}
+    if args.schedule_steps > 0:
+        schedule = run_leg('schedule_sweep', leg_schedule)
+        if rank == 0:
+            line['config']['schedule_sweep'] = schedule
+
+    # ---------------- the classic (one J row per attempt, HBM-bound) kernel on the equilibrated state ----------------
+    def leg_classic():
+        q_now = ann.get_spins()
+        ann_c = sq.dense_graph_annealer(W, sq.minimize, np.float32, n_trotters=m, device=dev)
+        ann_c.seed(1000 + rank)
+        ann_c.set_sweep_mode('classic')
+        ann_c.prepare()
+        ann_c.set_qset(q_now)
+        for _ in range(2):
+            ann_c.anneal_one_step(G_FIXED, BETA)
+        n_c = 6
+        c0 = ann_c.get_stats()['accepted']
+        ms_c = max_over_ranks(timed_steps(torch, stream, ann_c, [G_FIXED] * n_c, BETA, barrier))
+        acc_c = ann_c.get_stats()['accepted'] - c0
+        cs = ms_c / n_c * 1e-3
+        return {'ms_per_step': ms_c / n_c, 'value': world * attempts_per_step * n_c / (ms_c * 1e-3), 'unit': 'attempts/s', 'steps': n_c,
+                'acceptance_rate': acc_c / float(attempts_per_step * n_c), 'kernel': 'denseSweepKernel<float,true,16,false>',
+                'algorithmic_bytes_per_launch': algo_bytes,
+                'roofline': {'bound': 'hbm', 'achieved': algo_bytes / cs / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': algo_bytes / cs / 1e9 / peak,
+                             'note': 'algorithmic bytes (one row per attempt) / time; the share that misses L2 is in profiles/ (ncu)',
+                             'traffic_ncu': ncu_traffic_note('classic')}}
+    if not args.no_classic_leg and mode != 'classic':
+        line['classic'] = run_leg('classic', leg_classic)
+
+    if not args.no_secondary_legs:
+        line['secondary'] = run_leg('secondary', lambda: secondary_legs(args, torch, sq, dev, stream, ann, rank))
+
+    if not args.no_comm_legs:
+        line['comm'] = run_leg('comm', lambda: comm_legs(args, torch, dist, sq, dev, rank, local_rank, world, barrier))
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        def leg_cpu():
+            v, cores, sample, _, kind = cpu_reference_run(3, 1, budget_s=12.0, max_total_s=15.0)
+            return {'value': v, 'unit': 'attempts/s', 'cores': cores, 'kind': kind, 'sample': sample}
+        cb = run_leg('cpu_baseline', leg_cpu)
+        line['cpu_baseline'] = cb if 'error' not in cb else {'value': None, 'unit': 'attempts/s', 'cores': None, 'kind': 'port',
+                                                             'sample': 'failed: %s' % cb['error']}
+    emit()
     if world > 1:
         dist.destroy_process_group()
 

@@ -200,5 +200,34 @@ def test_two_rank_run_does_not_deadlock():
     assert 'error' not in line['comm']['ring_c5b'] and line['comm']['ring_c5b']['m'] == 512
 
 
+def _worker_hang():
+    """single rank; the replica leg never comes back: the watchdog has to print the line without the comm legs and end the process"""
+    import time
+    _install_fakes(_Patcher())
+    sys.modules['sqaod_b200.multigpu'].anneal_replicas = lambda *a, **k: time.sleep(3600)
+    sys.path.insert(0, ROOT)
+    import bench
+    bench.ClockSampler.start = lambda self: None
+    bench.ClockSampler.stop = lambda self: {'sm_mhz': 1965.0, 'sm_max_mhz': 1965.0, 'reasons': [], 'samples': 3}
+    sys.argv = ['bench.py', '--steps', '4', '--warmup', '3', '--N', '64', '--m', '8', '--equilibrate-seconds', '0.05', '--sustain-seconds', '0.01',
+                '--schedule-steps', '10', '--bf-N', '12', '--ring-N', '256', '--replicas-per-gpu', '2', '--bipartite-N', '32', '--no-cpu-baseline',
+                '--leg-timeout', '2']
+    bench.main()
+
+
+def test_a_leg_that_hangs_cannot_cost_the_line():
+    import subprocess
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE')}
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), '--worker-hang'], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-1500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, out.stdout[-1500:]
+    line = json.loads(lines[0])
+    assert 'comm' in line['watchdog'] and line['comm'] is None
+    assert line['value'] > 0 and line['e2e']['value'] > 0 and line['sustained']['steps'] >= 4 and line['secondary'] is not None
+
+
 if __name__ == '__main__' and '--worker' in sys.argv:
     _worker()
+if __name__ == '__main__' and '--worker-hang' in sys.argv:
+    _worker_hang()

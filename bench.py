@@ -160,6 +160,14 @@ def cpu_reference_run(steps, warmup, budget_s=15.0, max_total_s=150.0):
     is absent -- the bounded-sample port above is timed instead and the line says kind = "port"."""
     if not os.path.exists(REFCPU_GLUE):
         return cpu_port_run(steps, warmup, budget_s=budget_s)
+    try:
+        return _cpu_reference_compiled(steps, warmup, budget_s, max_total_s)
+    except Exception as e:      # e.g. the compiled glue does not load on this host: the port is the same algorithm (pinned against it)
+        sys.stderr.write('compiled reference unavailable (%s: %s); timing the oracle port instead\n' % (type(e).__name__, e))
+        return cpu_port_run(steps, warmup, budget_s=budget_s)
+
+
+def _cpu_reference_compiled(steps, warmup, budget_s, max_total_s):
     cores = len(os.sched_getaffinity(0))
     if os.environ.get('OMP_NUM_THREADS') in (None, '', '1'):    # torchrun pins it to 1 for N > 1; the reference sizes its pool from the affinity mask
         os.environ['OMP_NUM_THREADS'] = str(cores)

@@ -273,6 +273,7 @@ def main():
         statistics_case(24, 4, 4, A.coloring)
         statistics_case(64, 16, 20, A.coloring)
         statistics_case(48, 8, 12, A.sa_naive)
+        statistics_case(128, 32, 20, A.coloring)      # the shape of BASELINE config C1 (N = 128, m = 32), fp32, shortened schedule
     if FAILED:
         print('REFCPU_COMPARE_FAILED %d: %s' % (len(FAILED), '; '.join(FAILED)))
         return 1

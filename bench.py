@@ -462,9 +462,15 @@ def main():
     barrier()
     t_acc0 = ann.get_stats()['accepted']
     ms_tr = max_over_ranks(timed_steps(torch, stream, ann, [G_FIXED] * args.steps, BETA, barrier))
+    t_acc = ann.get_stats()['accepted'] - t_acc0
     transient = {'steps': args.steps, 'ms_per_step': ms_tr / args.steps, 'value': world * attempts_per_step * args.steps / (ms_tr * 1e-3),
-                 'unit': 'attempts/s', 'acceptance_rate': (ann.get_stats()['accepted'] - t_acc0) / float(attempts_per_step * args.steps),
+                 'unit': 'attempts/s', 'acceptance_rate': t_acc / float(attempts_per_step * args.steps),
                  'note': 'steps %d..%d after randomize_spin: acceptance still falling' % (args.warmup, args.warmup + args.steps - 1)}
+    if mode == 'field':     # same live traffic model as the headline's roofline (rank 0's counters): more accepted flips, more rows to move
+        tr_traffic = (t_acc / float(args.steps)) * (N * 4 + 32 * 32) + m * N * 4 + 2 * m * N
+        tr_peak = measured_peaks()[0]
+        transient['roofline'] = {'bound': 'latency', 'traffic': tr_traffic, 'achieved': tr_traffic / (ms_tr / args.steps * 1e-3) / 1e9, 'peak': tr_peak,
+                                 'unit': 'GB/s', 'frac': tr_traffic / (ms_tr / args.steps * 1e-3) / 1e9 / tr_peak}
 
     # ---------------- the reference protocol's warm-up phase: untimed steps at the operating point until the chain is stationary ----------------
     equil_steps = 0

@@ -131,3 +131,23 @@ def test_preference_and_algorithm_names_equal_the_reference_library():
     for s in sorted(n for n in names if n) + [b'', b'nonsense', b'Coloring', b'tile_size', b'n_trotters', b'sa_naive', b'default']:
         assert s2a[0](s) == s2a[1](s), s
         assert s2p[0](s) == s2p[1](s), s
+
+
+def test_product_library_carries_blackwell_sass():
+    """What `cuobjdump -sass` of libsqaod_b200.so shows (B200_PROFILING.md's mnemonic table): the tcgen05 GEMM (UTCHMMA, LDTM), TMA tensor
+    and bulk copies (UTMALDG, UBLKCP), mbarrier traffic (SYNCS), cp.async gathers (LDGSTS), packed fp32 adds (FADD2) -- and no legacy
+    mma.sync path (every HMMA in the listing is the tail of a UTCHMMA).  Guards the build flags: a library compiled for another
+    architecture would still load here."""
+    import shutil
+    import subprocess
+    exe = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(exe):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([exe, '-sass', os.path.join(ROOT, 'sqaod_b200', 'lib', 'libsqaod_b200.so')], capture_output=True, text=True,
+                          timeout=600).stdout
+    count = lambda k: sum(1 for l in sass.splitlines() if k in l)
+    for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG', 'UBLKCP', 'SYNCS', 'LDGSTS', 'FADD2'):
+        assert count(mnemonic) > 0, mnemonic
+    assert count('HMMA') == count('UTCHMMA')
+    archs = [l.split('=')[1].strip() for l in sass.splitlines() if l.startswith('arch =')]
+    assert archs.count('sm_100a') >= 7 and set(archs) <= {'sm_100a', 'sm_52'}     # sm_52: nvcc's empty device-link stub, no code in it

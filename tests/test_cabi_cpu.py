@@ -151,3 +151,12 @@ def test_product_library_carries_blackwell_sass():
     assert count('HMMA') == count('UTCHMMA')
     archs = [l.split('=')[1].strip() for l in sass.splitlines() if l.startswith('arch =')]
     assert archs.count('sm_100a') >= 7 and set(archs) <= {'sm_100a', 'sm_52'}     # sm_52: nvcc's empty device-link stub, no code in it
+
+
+def test_product_library_links_no_vendor_math_or_collective_library():
+    """north_star: "no cuBLAS, Triton or CPU fallback inside the path" -- the library's dynamic dependencies are the C/C++ runtime only
+    (the CUDA runtime is linked statically); nothing of cuBLAS, cuRAND, cuDNN, cuSPARSE, NCCL or the oracle."""
+    import subprocess
+    out = subprocess.run(['ldd', os.path.join(ROOT, 'sqaod_b200', 'lib', 'libsqaod_b200.so')], capture_output=True, text=True).stdout.lower()
+    for name in ('cublas', 'curand', 'cudnn', 'cusparse', 'cusolver', 'nccl', 'liboracle', 'sqaodc', 'torch'):
+        assert name not in out, name

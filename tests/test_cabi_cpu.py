@@ -160,3 +160,68 @@ def test_product_library_links_no_vendor_math_or_collective_library():
     out = subprocess.run(['ldd', os.path.join(ROOT, 'sqaod_b200', 'lib', 'libsqaod_b200.so')], capture_output=True, text=True).stdout.lower()
     for name in ('cublas', 'curand', 'cudnn', 'cusparse', 'cusolver', 'nccl', 'liboracle', 'sqaodc', 'torch'):
         assert name not in out, name
+
+
+@pytest.mark.parametrize('dt', [0, 1])
+def test_searcher_preferences_behave_like_the_reference_solver(lib, dt):
+    """Backend-independent host logic of the solver base classes (sqaodc/common/Solver.cpp:190-250), ours through the C ABI against the
+    reference's own library through its own Python package (oracle/_ref): how requested tile sizes are adjusted, what get_preferences
+    reports for a fresh searcher, and that non-positive sizes are refused."""
+    import subprocess
+    import sys
+    import json
+    suite = os.path.join(ROOT, 'oracle', '_ref', 'refsuite')
+    if not os.path.exists(os.path.join(suite, 'glue_cpu', 'cpu_dg_bf_searcher.so')):
+        pytest.skip('reference CPU build absent (run `make -C oracle refcpu` where /root/reference exists)')
+    sizes = [1, 255, 256, 257, 1000, 4096, 70000]
+    code = r'''
+import sys, json, warnings
+warnings.simplefilter('ignore')
+import numpy as np
+sys.path.insert(0, sys.argv[1] + '/tests')
+import refsuite_runner
+sq = refsuite_runner.assemble('cpu')
+dtype = np.float32 if sys.argv[2] == '0' else np.float64
+out = {'dg': [], 'bg0': [], 'bg1': []}
+s = sq.cpu.dense_graph_bf_searcher(dtype=dtype)
+b = sq.cpu.bipartite_graph_bf_searcher(dtype=dtype)
+out['fresh_dg'] = {k: v for k, v in s.get_preferences().items() if k in ('algorithm', 'precision')}
+out['fresh_bg'] = {k: v for k, v in b.get_preferences().items() if k in ('algorithm', 'precision')}
+for v in json.loads(sys.argv[3]):
+    s.set_preferences(tile_size=v); out['dg'].append(s.get_preferences()['tile_size'])
+    b.set_preferences(tile_size_0=v); out['bg0'].append(b.get_preferences()['tile_size_0'])
+    b.set_preferences(tile_size_1=v); out['bg1'].append(b.get_preferences()['tile_size_1'])
+def refused(f):
+    try:
+        f()
+    except Exception:
+        return True
+    return False
+out['neg'] = [refused(lambda: s.set_preferences(tile_size=0)), refused(lambda: b.set_preferences(tile_size_0=-3))]
+print('REF ' + json.dumps(out))
+'''
+    run = subprocess.run([sys.executable, '-c', code, ROOT, str(dt), json.dumps(sizes)], capture_output=True, text=True, timeout=300)
+    ref = json.loads([l for l in run.stdout.splitlines() if l.startswith('REF ')][0][4:])
+    L = lib.lib
+    buf = C.create_string_buffer(512)
+
+    def prefs(getter, h):
+        assert getter(h, buf, 512, dt) == 0
+        return dict(kv.split('=') for kv in buf.value.decode().split(';'))
+    s, b = C.c_void_p(), C.c_void_p()
+    assert L.sqb_dg_bf_searcher_new(C.byref(s), dt) == 0 and L.sqb_bg_bf_searcher_new(C.byref(b), dt) == 0
+    p = prefs(L.sqb_dg_bf_searcher_get_preferences, s)
+    assert {k: p[k] for k in ('algorithm', 'precision')} == ref['fresh_dg']
+    p = prefs(L.sqb_bg_bf_searcher_get_preferences, b)
+    assert {k: p[k] for k in ('algorithm', 'precision')} == ref['fresh_bg']
+    for i, v in enumerate(sizes):
+        assert L.sqb_dg_bf_searcher_set_preference(s, b'tile_size', None, v, dt) == 0
+        assert int(prefs(L.sqb_dg_bf_searcher_get_preferences, s)['tile_size']) == ref['dg'][i], v
+        assert L.sqb_bg_bf_searcher_set_preference(b, b'tile_size_0', None, v, dt) == 0
+        assert int(prefs(L.sqb_bg_bf_searcher_get_preferences, b)['tile_size_0']) == ref['bg0'][i], v
+        assert L.sqb_bg_bf_searcher_set_preference(b, b'tile_size_1', None, v, dt) == 0
+        assert int(prefs(L.sqb_bg_bf_searcher_get_preferences, b)['tile_size_1']) == ref['bg1'][i], v
+    assert ref['neg'] == [True, True]
+    assert L.sqb_dg_bf_searcher_set_preference(s, b'tile_size', None, 0, dt) != 0
+    assert L.sqb_bg_bf_searcher_set_preference(b, b'tile_size_0', None, -3, dt) != 0
+    assert L.sqb_dg_bf_searcher_delete(s, dt) == 0 and L.sqb_bg_bf_searcher_delete(b, dt) == 0

@@ -16,7 +16,7 @@ Further legs of the same line (SURVEY.md 8d asks for them because the field-mode
   transient              the K steps that follow randomize_spin + W warm-up steps WITHOUT the protocol's warm-up phase (acceptance
                          still falling: the sweep's worst case at this operating point)
   sustained              >= 2 s of back-to-back steps at the fixed point, with its own clock samples
-  config.schedule_sweep  a fresh anneal over the reference example's whole schedule G 5 -> 0.01 (geometric), beta = 50
+  schedule_sweep         a fresh anneal over the reference example's whole schedule G 5 -> 0.01 (geometric), beta = 50
                          (sqaodpy/example/dense_graph_annealer.py:60-70), with the acceptance rate per fifth of the schedule
   classic                the one-J-row-per-attempt kernel (HBM-bound) on the same state
   secondary              the tensor-core rows on one GPU: calculate_E at C2 and the bipartite annealOneStep at C3 (N0=N1=4096, m=512), with
@@ -41,6 +41,16 @@ sys.path.insert(0, ROOT)
 N_SPINS, M_TROTTERS = 8192, 512
 G_FIXED, BETA = 0.01, 1.0 / 0.02          # sqaodpy/benchmark/benchmark.py:10-11
 W_SEED = 1133557                          # sqaodc/tests/perf.cpp:21
+
+
+def workload_config(N=N_SPINS, m=M_TROTTERS):
+    """What is measured, in words and numbers that do not depend on the run: printed identically by both arms (this library and
+    --impl reference), so the two lines can be matched on it.  Everything a run finds out about itself goes under `run`."""
+    return {'workload': 'dense-graph SQA N=%d m=%d fp32 random QUBO (BASELINE.json configs[1]); at N > 1 GPUs one independent replica per GPU' % (N, m),
+            'G': G_FIXED, 'beta': BETA, 'algorithm': 'coloring',
+            'protocol': 'sqaodpy/benchmark/benchmark.py:9-48: randomize_spin, an untimed warm-up phase of anneal_one_step at the operating point '
+                        '(the reference: batches until one takes >= 5 s), then W warm-up steps and K timed steps',
+            'l2': 'J is %d MiB > 126 MB L2 and rows are drawn at random, no flush needed' % (N * N * 4 >> 20)}
 
 
 def make_problem(N, seed=W_SEED):
@@ -209,7 +219,7 @@ def run_reference(args, rank):
         'impl': 'reference', 'metric': 'spin-flip attempts/sec (dense SQA N=8192 m=512)', 'value': value, 'unit': 'attempts/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'dense-graph SQA N=8192 m=512 fp32 random QUBO (BASELINE.json configs[1])', 'G': G_FIXED, 'beta': BETA},
+        'config': workload_config(),
         'cpu_baseline': {'value': value, 'unit': 'attempts/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'attempts/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -549,24 +559,19 @@ def main():
             'metric': 'spin-flip attempts/sec (dense SQA N=8192 m=512)', 'value': value, 'unit': 'attempts/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'dense-graph SQA N=%d m=%d fp32 random QUBO (BASELINE.json configs[1]); one independent '
-                                   'replica per GPU' % (N, m), 'G': G_FIXED, 'beta': BETA, 'algorithm': 'coloring',
-                       'sweep_mode': mode + (' (local fields h + 2 J.q from the tensor-core spin GEMM every step, kept in shared memory, one J row '
-                                             'streamed per ACCEPTED flip; one accept-chain warp per trotter)' if mode == 'field' else ' (one J row streamed per attempt)'),
-                       'l2': 'J is %d MiB > 126 MB L2 and rows are drawn at random, no flush needed' % (N * N * 4 >> 20),
-                       'acceptance_rate': acc_rate,
-                       'protocol': 'sqaodpy/benchmark/benchmark.py:9-48: randomize_spin, untimed warm-up phase at the operating point (here %d '
-                                   'steps = %.1f s; the reference: batches until one takes >= 5 s), %d warm-up steps, %d timed steps; the '
-                                   '"transient" leg times the same K steps without the warm-up phase' % (
-                                       equil_steps, args.equilibrate_seconds, args.warmup, args.steps),
-                       'equilibration_steps': equil_steps,
-                       'flag_waits': stats1['flag_waits'] - stats0['flag_waits'],
-                       'device': {'sms': sms, 'sm_mhz_used_for_cycle_conversion': mhz},
-                       # chain warp 0 and field warp 0 of every CTA, averaged: where a step goes
-                       'ms_per_step_per_cta': {'chain_busy': cyc_ms('barrier_cycles_chain'), 'chain_wait_fields': cyc_ms('chain_wait_rows_cycles'),
-                                               'chain_wait_neighbour_ctas': cyc_ms('chain_wait_neighbour_cycles'),
-                                               'field_warp_busy': cyc_ms('barrier_cycles_dot')},
-                       'schedule_sweep': None},
+            'config': workload_config(N, m),
+            # what this run found out about itself
+            'run': {'sweep_mode': mode + (' (local fields h + 2 J.q from the tensor-core spin GEMM, carried in shared memory, one J row streamed per '
+                                          'ACCEPTED flip; one accept-chain warp per trotter)' if mode == 'field' else ' (one J row streamed per attempt)'),
+                    'acceptance_rate': acc_rate,
+                    'equilibration_steps': equil_steps, 'equilibration_seconds': args.equilibrate_seconds,
+                    'flag_waits': stats1['flag_waits'] - stats0['flag_waits'],
+                    'device': {'sms': sms, 'sm_mhz_used_for_cycle_conversion': mhz},
+                    # chain warp 0 and field warp 0 of every CTA, averaged: where a step goes
+                    'ms_per_step_per_cta': {'chain_busy': cyc_ms('barrier_cycles_chain'), 'chain_wait_fields': cyc_ms('chain_wait_rows_cycles'),
+                                            'chain_wait_neighbour_ctas': cyc_ms('chain_wait_neighbour_cycles'),
+                                            'field_warp_busy': cyc_ms('barrier_cycles_dot')}},
+            'schedule_sweep': None,
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'attempts/s', 'h2d_bytes_per_step': m * N, 'd2h_bytes_per_step': m * N + m * 4,
                     'steps': e2e_steps, 'E_min': float(np.min(E))},
@@ -644,7 +649,7 @@ def main():
     if args.schedule_steps > 0:
         schedule = run_leg('schedule_sweep', leg_schedule)
         if rank == 0:
-            line['config']['schedule_sweep'] = schedule
+            line['schedule_sweep'] = schedule
 
     # ---------------- the classic (one J row per attempt, HBM-bound) kernel on the equilibrated state ----------------
     def leg_classic():

@@ -131,7 +131,9 @@ def test_bench_line_carries_the_contract_keys(monkeypatch):
     assert set(line['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
     assert line['e2e']['h2d_bytes_per_step'] == 64 * 8 and line['e2e']['d2h_bytes_per_step'] == 64 * 8 + 8 * 4
     assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
-    assert line['config']['equilibration_steps'] > 0 and 'workload' in line['config'] and line['config']['schedule_sweep']['steps'] == 10
+    assert line['run']['equilibration_steps'] > 0 and 'workload' in line['config'] and line['schedule_sweep']['steps'] == 10
+    import bench
+    assert line['config'] == bench.workload_config(64, 8)          # nothing run-dependent in `config`: both arms print the same one
     assert line['transient']['steps'] == 4
     for leg in ('calculate_E_c2', 'bipartite_c3'):
         assert 'error' not in line['secondary'][leg], line['secondary'][leg]
@@ -153,6 +155,7 @@ def test_quick_mode_and_reference_arm_keys(monkeypatch):
     assert ref['impl'] == 'reference' and ref['steps'] == 2 and ref['cpu_baseline']['kind'] in ('reference', 'port')
     assert ref['e2e'] == {'value': ref['value'], 'unit': 'attempts/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert ref['cpu_baseline']['cores'] >= 1 and ref['value'] > 0
+    assert ref['config'] == bench.workload_config()
 
 
 def _worker():

@@ -6,6 +6,9 @@
                                                          sqaodpy/sqaod/cuda/src/cuda_*.cpp), compiled unmodified against
                                                          include/sqaodc/sqaodc.h and linked to libsqaod_b200.so
     python tests/refsuite_runner.py cext [pytest args]   sqaod_b200.cext (the ctypes restatement of the same method tables)
+    python tests/refsuite_runner.py full [pytest args]   the whole package as a user imports it: sqaod.py, sqaod.cpu = the reference's own CPU
+                                                         back end (below) and sqaod.cuda = the reference glue over libsqaod_b200.so, all of the
+                                                         reference's test classes in one process
     python tests/refsuite_runner.py cpu  [pytest args]   no GPU: the reference's CPU back end itself (`make -C oracle refcpu`: sqaodc/common +
                                                          sqaodc/cpu + the cpu_*.cpp glue, compiled unmodified against oracle/eigen_standin) under
                                                          the reference's own CPU and pure-Python test classes -- checks that build, which the
@@ -54,7 +57,7 @@ def assemble(binding):
         return pkg
     for name in CEXT:
         full = 'sqaod.cuda.' + name
-        if binding == 'glue':
+        if binding in ('glue', 'full'):
             spec = importlib.util.spec_from_file_location(full, os.path.join(SUITE, 'glue', name + '.so'))
             mod = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(mod)
@@ -62,6 +65,10 @@ def assemble(binding):
             mod = importlib.import_module('sqaod_b200.cext.' + name)
         sys.modules[full] = mod
     pkg.cuda = importlib.import_module('sqaod.cuda')
+
+    if binding == 'full':
+        load_reference_cpu(pkg)
+        return pkg
 
     class _NoCPU(types.ModuleType):
         def __getattr__(self, name):
@@ -89,7 +96,7 @@ def main():
         return 0
     assemble(binding)
     import pytest
-    select = 'not cuda and not version' if binding == 'cpu' else 'cuda and not version'
+    select = {'cpu': 'not cuda and not version', 'full': 'not version'}.get(binding, 'cuda and not version')
     args = [os.path.join(SUITE, 'tests'), '-q', '-p', 'no:cacheprovider', '-k', select, '--rootdir', SUITE,
             '-o', 'python_files=test_*.py', '-rfE', '--tb=short'] + sys.argv[2:]
     rc = pytest.main(args)

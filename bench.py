@@ -20,7 +20,8 @@ Further legs of the same line (SURVEY.md 8d asks for them because the field-mode
                          (sqaodpy/example/dense_graph_annealer.py:60-70), with the acceptance rate per fifth of the schedule
   classic                the one-J-row-per-attempt kernel (HBM-bound) on the same state
   secondary              the tensor-core rows on one GPU: calculate_E at C2 and the bipartite annealOneStep at C3 (N0=N1=4096, m=512), with
-                         their tensor roofline (algorithmic flops / time against the measured dense-bf16 peak / 3)
+                         their tensor roofline (algorithmic flops / time against the measured dense-bf16 peak / 3); and config C1, the
+                         reference's tutorial anneal (N=128, m=32, fp64, 619 steps), here and through the reference's own sqaod.cpu
   comm                   what communicates: brute force N=40 sharded over the ranks + NCCL min/gather merge,
                          the ring-sharded N=32768 sweep (256 trotters per GPU, NVLink hand-off), 512 replicas per GPU of N=1024 m=128
 At N > 1 every GPU anneals its own replica of the headline problem with its own seed ("replicas only"): scaling weak.
@@ -386,6 +387,46 @@ def secondary_legs(args, torch, sq, dev, stream, ann, rank):
         del bg
     except Exception as e:
         out['bipartite_c3'] = {'error': str(e)[:300]}
+    try:    # BASELINE.json configs[0] (C1): the reference's tutorial anneal, N = 128, m = 32, fp64, G 5 -> 0.01 with G *= 0.99 (619 steps),
+            # beta = 50, seed 13255 (sqaodpy/example/dense_graph_annealer.py:22-70): wall clock here, and through the reference's own
+            # sqaod.cpu (compiled from its sources, oracle/_ref) on the host -- the one config the reference itself runs on a CPU
+        Nc, mc = 128, 32
+        rng = np.random.default_rng(13255)
+        A = rng.random((Nc, Nc)) - 0.5
+        Wc = np.triu(A) + np.triu(A, 1).T
+        Gs, G = [], 5.0
+        while 0.01 <= G:
+            Gs.append(G)
+            G *= 0.99
+
+        def tutorial(factory, **kw):
+            a = factory(Wc, kw.pop('optimize'), np.float64, n_trotters=mc, **kw)
+            a.seed(13255); a.prepare(); a.randomize_spin()
+            t0 = time.perf_counter()
+            for g in Gs:
+                a.anneal_one_step(g, BETA)
+            E = np.asarray(a.get_E())                         # waits for the device
+            return time.perf_counter() - t0, float(E.min()), float(E.mean())
+        tutorial(sq.dense_graph_annealer, optimize=sq.minimize, device=dev)       # first pass: module load, allocations
+        sec, emin, emean = tutorial(sq.dense_graph_annealer, optimize=sq.minimize, device=dev)
+        c1 = {'N': Nc, 'm': mc, 'dtype': 'f64', 'steps': len(Gs), 'seconds': sec, 'attempts_per_s': len(Gs) * Nc * mc / sec, 'E_min': emin, 'E_mean': emean,
+              'note': 'wall clock of the whole tutorial loop incl. the final get_E; launch-latency bound at this size'}
+        if rank == 0 and os.path.exists(REFCPU_GLUE):
+            try:
+                sys.path.insert(0, os.path.join(ROOT, 'tests'))
+                import refsuite_runner
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    ref = refsuite_runner.assemble('cpu')
+                rsec, remin, remean = tutorial(ref.cpu.dense_graph_annealer, optimize=ref.minimize)
+                c1['reference_cpu'] = {'seconds': rsec, 'attempts_per_s': len(Gs) * Nc * mc / rsec, 'E_min': remin, 'E_mean': remean,
+                                       'cores': len(os.sched_getaffinity(0)), 'kind': 'reference'}
+            except Exception as e:
+                c1['reference_cpu'] = {'error': str(e)[:300]}
+        out['c1_tutorial'] = c1
+    except Exception as e:
+        out['c1_tutorial'] = {'error': str(e)[:300]}
     return out
 
 

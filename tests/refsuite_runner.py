@@ -31,7 +31,19 @@ CPU_CEXT = ['cpu_dg_annealer', 'cpu_bg_annealer', 'cpu_dg_bf_searcher', 'cpu_bg_
 CEXT = ['cuda_device', 'cuda_dg_annealer', 'cuda_bg_annealer', 'cuda_dg_bf_searcher', 'cuda_bg_bf_searcher', 'cuda_formulas']
 
 
+_ASSEMBLED = {}
+
+
 def assemble(binding):
+    if binding in _ASSEMBLED:       # extension modules load once per process: a second call hands back the same package
+        sys.modules['sqaod'] = _ASSEMBLED[binding]
+        return _ASSEMBLED[binding]
+    pkg = _assemble(binding)
+    _ASSEMBLED[binding] = pkg
+    return pkg
+
+
+def _assemble(binding):
     sys.path.insert(0, SUITE)
     if binding == 'cext':
         sys.path.insert(1, ROOT)

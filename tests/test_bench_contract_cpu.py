@@ -82,6 +82,7 @@ def _install_fakes(monkeypatch):
     sq.Device = Device
     sq.set_active_device = lambda d: None
     sq.dense_graph_annealer = lambda W, opt, dtype, n_trotters=None, device=None: _FakeAnnealer(0 if W is None else W.shape[0], n_trotters or 1)
+    sq.maximize = 1
     sq.bipartite_graph_annealer = lambda b0, b1, W, opt, dtype, n_trotters=None, device=None: _FakeAnnealer(W.shape[1], n_trotters or 1)
     mg = types.ModuleType('sqaod_b200.multigpu')
     mg.sharded_dense_bf_search = lambda W, opt, dtype: (np.float32(-1.5), [np.zeros(W.shape[0], np.int8)])
@@ -135,6 +136,11 @@ def test_bench_line_carries_the_contract_keys(monkeypatch):
     import bench
     assert line['config'] == bench.workload_config(64, 8)          # nothing run-dependent in `config`: both arms print the same one
     assert line['transient']['steps'] == 4
+    c1 = line['secondary']['c1_tutorial']
+    assert 'error' not in c1 and c1['steps'] == 619 and c1['N'] == 128 and c1['m'] == 32
+    if 'reference_cpu' in c1:           # present when oracle/_ref holds the compiled reference: it really runs the tutorial here
+        assert 'error' not in c1['reference_cpu'], c1['reference_cpu']
+        assert c1['reference_cpu']['E_min'] < -200 and c1['reference_cpu']['kind'] == 'reference'
     for leg in ('calculate_E_c2', 'bipartite_c3'):
         assert 'error' not in line['secondary'][leg], line['secondary'][leg]
         assert line['secondary'][leg]['roofline']['bound'] == 'tensor' and line['secondary'][leg]['roofline']['frac'] > 0

@@ -45,6 +45,8 @@ def test_reference_python_suite_all_backends_in_one_process():
         text, err = out.stdout, out.stderr
     except subprocess.TimeoutExpired as e:
         text, err = (e.stdout or b'').decode(errors='replace') if isinstance(e.stdout, bytes) else (e.stdout or ''), 'timeout'
+    except Exception as e:
+        text, err = '', '%s: %s' % (type(e).__name__, e)
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'refsuite_full.log'), 'w') as f:
         f.write(text + err)

@@ -21,7 +21,8 @@ Further legs of the same line (SURVEY.md 8d asks for them because the field-mode
   classic                the one-J-row-per-attempt kernel (HBM-bound) on the same state
   secondary              the tensor-core rows on one GPU: calculate_E at C2 and the bipartite annealOneStep at C3 (N0=N1=4096, m=512), with
                          their tensor roofline (algorithmic flops / time against the measured dense-bf16 peak / 3); and config C1, the
-                         reference's tutorial anneal (N=128, m=32, fp64, 619 steps), here and through the reference's own sqaod.cpu
+                         reference's tutorial anneal (N=128, m=32, fp64, 619 steps) -- the same loop through the reference's own
+                         sqaod.cpu is part of cpu_baseline
   comm                   what communicates: brute force N=40 sharded over the ranks + NCCL min/gather merge,
                          the ring-sharded N=32768 sweep (256 trotters per GPU, NVLink hand-off), 512 replicas per GPU of N=1024 m=128
 At N > 1 every GPU anneals its own replica of the headline problem with its own seed ("replicas only"): scaling weak.
@@ -337,6 +338,46 @@ def comm_legs(args, torch, dist, sq, dev, rank, local_rank, world, barrier):
     return out
 
 
+def c1_problem():
+    """BASELINE.json configs[0]: W ~ U(-0.5, 0.5) symmetric (seed 13255), and the tutorial's schedule G = 5, 5 * 0.99, ... >= 0.01"""
+    rng = np.random.default_rng(13255)
+    A = rng.random((128, 128)) - 0.5
+    Gs, G = [], 5.0
+    while 0.01 <= G:
+        Gs.append(G)
+        G *= 0.99
+    return np.triu(A) + np.triu(A, 1).T, Gs
+
+
+def c1_tutorial(factory, W, Gs, **kw):
+    """the loop of sqaodpy/example/dense_graph_annealer.py:44-70 on any package with the reference's solver API; (seconds, E_min, E_mean)"""
+    a = factory(W, kw.pop('optimize'), np.float64, n_trotters=32, **kw)
+    a.seed(13255)
+    a.prepare()
+    a.randomize_spin()
+    t0 = time.perf_counter()
+    for g in Gs:
+        a.anneal_one_step(g, BETA)
+    E = np.asarray(a.get_E())                             # waits for the device
+    return time.perf_counter() - t0, float(E.min()), float(E.mean())
+
+
+def c1_reference_cpu():
+    """C1 through the reference's own sqaod.cpu (compiled from its sources, oracle/_ref): part of the cpu_baseline leg"""
+    if not os.path.exists(REFCPU_GLUE):
+        return None
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import refsuite_runner
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = refsuite_runner.assemble('cpu')
+    Wc, Gs = c1_problem()
+    sec, emin, emean = c1_tutorial(ref.cpu.dense_graph_annealer, Wc, Gs, optimize=ref.minimize)
+    return {'N': 128, 'm': 32, 'dtype': 'f64', 'steps': len(Gs), 'seconds': sec, 'attempts_per_s': len(Gs) * 128 * 32 / sec, 'E_min': emin,
+            'E_mean': emean, 'cores': len(os.sched_getaffinity(0)), 'kind': 'reference'}
+
+
 def secondary_legs(args, torch, sq, dev, stream, ann, rank):
     """The tensor-core rows of the path (a6, a7) on one GPU, so that they have a driver-side number next to the
     headline: calculate_E at C2 (on the headline annealer's state) and the bipartite annealOneStep at C3, both through the split-bf16
@@ -388,43 +429,15 @@ def secondary_legs(args, torch, sq, dev, stream, ann, rank):
     except Exception as e:
         out['bipartite_c3'] = {'error': str(e)[:300]}
     try:    # BASELINE.json configs[0] (C1): the reference's tutorial anneal, N = 128, m = 32, fp64, G 5 -> 0.01 with G *= 0.99 (619 steps),
-            # beta = 50, seed 13255 (sqaodpy/example/dense_graph_annealer.py:22-70): wall clock here, and through the reference's own
-            # sqaod.cpu (compiled from its sources, oracle/_ref) on the host -- the one config the reference itself runs on a CPU
-        Nc, mc = 128, 32
-        rng = np.random.default_rng(13255)
-        A = rng.random((Nc, Nc)) - 0.5
-        Wc = np.triu(A) + np.triu(A, 1).T
-        Gs, G = [], 5.0
-        while 0.01 <= G:
-            Gs.append(G)
-            G *= 0.99
-
-        def tutorial(factory, **kw):
-            a = factory(Wc, kw.pop('optimize'), np.float64, n_trotters=mc, **kw)
-            a.seed(13255); a.prepare(); a.randomize_spin()
-            t0 = time.perf_counter()
-            for g in Gs:
-                a.anneal_one_step(g, BETA)
-            E = np.asarray(a.get_E())                         # waits for the device
-            return time.perf_counter() - t0, float(E.min()), float(E.mean())
-        tutorial(sq.dense_graph_annealer, optimize=sq.minimize, device=dev)       # first pass: module load, allocations
-        sec, emin, emean = tutorial(sq.dense_graph_annealer, optimize=sq.minimize, device=dev)
-        c1 = {'N': Nc, 'm': mc, 'dtype': 'f64', 'steps': len(Gs), 'seconds': sec, 'attempts_per_s': len(Gs) * Nc * mc / sec, 'E_min': emin, 'E_mean': emean,
-              'note': 'wall clock of the whole tutorial loop incl. the final get_E; launch-latency bound at this size'}
-        if rank == 0 and os.path.exists(REFCPU_GLUE):
-            try:
-                sys.path.insert(0, os.path.join(ROOT, 'tests'))
-                import refsuite_runner
-                import warnings
-                with warnings.catch_warnings():
-                    warnings.simplefilter('ignore')
-                    ref = refsuite_runner.assemble('cpu')
-                rsec, remin, remean = tutorial(ref.cpu.dense_graph_annealer, optimize=ref.minimize)
-                c1['reference_cpu'] = {'seconds': rsec, 'attempts_per_s': len(Gs) * Nc * mc / rsec, 'E_min': remin, 'E_mean': remean,
-                                       'cores': len(os.sched_getaffinity(0)), 'kind': 'reference'}
-            except Exception as e:
-                c1['reference_cpu'] = {'error': str(e)[:300]}
-        out['c1_tutorial'] = c1
+            # beta = 50, seed 13255 (sqaodpy/example/dense_graph_annealer.py:22-70), the one config the reference itself runs on a CPU: wall
+            # clock here; the cpu_baseline leg runs the same loop through the reference's own sqaod.cpu
+        Wc, Gs = c1_problem()
+        c1_tutorial(sq.dense_graph_annealer, Wc, Gs, optimize=sq.minimize, device=dev)        # first pass: allocations, module load
+        sec, emin, emean = c1_tutorial(sq.dense_graph_annealer, Wc, Gs, optimize=sq.minimize, device=dev)
+        out['c1_tutorial'] = {'N': 128, 'm': 32, 'dtype': 'f64', 'steps': len(Gs), 'seconds': sec, 'attempts_per_s': len(Gs) * 128 * 32 / sec,
+                              'E_min': emin, 'E_mean': emean,
+                              'note': 'wall clock of the whole tutorial loop incl. the final get_E; launch-latency bound at this size; the same '
+                                      'loop through the reference CPU solver: cpu_baseline.c1_tutorial'}
     except Exception as e:
         out['c1_tutorial'] = {'error': str(e)[:300]}
     return out
@@ -725,7 +738,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         def leg_cpu():
             v, cores, sample, _, kind = cpu_reference_run(3, 1, budget_s=12.0, max_total_s=15.0)
-            return {'value': v, 'unit': 'attempts/s', 'cores': cores, 'kind': kind, 'sample': sample}
+            cb = {'value': v, 'unit': 'attempts/s', 'cores': cores, 'kind': kind, 'sample': sample}
+            if not args.no_secondary_legs:
+                try:        # config C1 on the host, next to secondary.c1_tutorial
+                    cb['c1_tutorial'] = c1_reference_cpu()
+                except Exception as e:
+                    cb['c1_tutorial'] = {'error': str(e)[:300]}
+            return cb
         cb = run_leg('cpu_baseline', leg_cpu)
         line['cpu_baseline'] = cb if 'error' not in cb else {'value': None, 'unit': 'attempts/s', 'cores': None, 'kind': 'port',
                                                              'sample': 'failed: %s' % cb['error']}

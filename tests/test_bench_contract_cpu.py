@@ -138,9 +138,10 @@ def test_bench_line_carries_the_contract_keys(monkeypatch):
     assert line['transient']['steps'] == 4
     c1 = line['secondary']['c1_tutorial']
     assert 'error' not in c1 and c1['steps'] == 619 and c1['N'] == 128 and c1['m'] == 32
-    if 'reference_cpu' in c1:           # present when oracle/_ref holds the compiled reference: it really runs the tutorial here
-        assert 'error' not in c1['reference_cpu'], c1['reference_cpu']
-        assert c1['reference_cpu']['E_min'] < -200 and c1['reference_cpu']['kind'] == 'reference'
+    import bench
+    ref_c1 = bench.c1_reference_cpu()   # what the cpu_baseline leg adds (None without oracle/_ref): the compiled reference really runs the tutorial here
+    if ref_c1 is not None:
+        assert ref_c1['steps'] == 619 and ref_c1['E_min'] < -200 and ref_c1['kind'] == 'reference'
     for leg in ('calculate_E_c2', 'bipartite_c3'):
         assert 'error' not in line['secondary'][leg], line['secondary'][leg]
         assert line['secondary'][leg]['roofline']['bound'] == 'tensor' and line['secondary'][leg]['roofline']['frac'] > 0
@@ -162,6 +163,21 @@ def test_quick_mode_and_reference_arm_keys(monkeypatch):
     assert ref['e2e'] == {'value': ref['value'], 'unit': 'attempts/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert ref['cpu_baseline']['cores'] >= 1 and ref['value'] > 0
     assert ref['config'] == bench.workload_config()
+
+
+def test_cpu_baseline_leg_runs_inside_the_main_arm(monkeypatch):
+    """the one leg of the GPU arm that executes oracle/ (permitted: cpu_baseline), at a reduced size: the C2 sample and config C1"""
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setattr(bench, 'N_SPINS', 256)
+    monkeypatch.setattr(bench, 'M_TROTTERS', 16)
+    line = _run(monkeypatch, ['--steps', '3', '--N', '64', '--m', '8', '--equilibrate-seconds', '0.02', '--sustain-seconds', '0', '--schedule-steps', '0',
+                              '--no-classic-leg', '--no-comm-legs', '--bipartite-N', '32'])
+    cb = line['cpu_baseline']
+    assert cb['value'] > 0 and cb['kind'] in ('reference', 'port') and cb['cores'] >= 1
+    if cb['kind'] == 'reference':
+        assert cb['c1_tutorial']['steps'] == 619 and cb['c1_tutorial']['E_min'] < -200
+    assert line['secondary']['c1_tutorial']['steps'] == 619
 
 
 def _worker():
